@@ -1,0 +1,206 @@
+"""ctypes binding of the C-ABI in include/mandelbrot_b200.h (libmandelbrot_b200.so).
+
+There is no fallback of any kind here: if the shared library is missing it is built with nvcc
+(distributedmandelbrot_b200.build); if that fails, or a compute entry point is called without
+a usable CUDA device, a NativeError is raised.  The CPU oracle under oracle/ is test
+infrastructure and is never imported from this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+MB_OK = 0
+MB_ERR_INVALID, MB_ERR_CUDA, MB_ERR_NOMEM, MB_ERR_STATE, MB_ERR_SYS = -1, -2, -3, -4, -5
+DTYPE_F64, DTYPE_F32 = 0, 1
+DTYPES = {"f64": DTYPE_F64, "f32": DTYPE_F32, DTYPE_F64: DTYPE_F64, DTYPE_F32: DTYPE_F32}
+CHUNK_DEFINITION = 4096   # DataChunk.dataChunkRange (DataChunk.cs:20) ; .py:80
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmandelbrot_b200: {msg} (status {code})")
+        self.code = code
+
+
+class InvalidArgument(NativeError, ValueError):
+    """MB_ERR_INVALID -- mirrors the ArgumentException of the DataChunk ctor (DataChunk.cs:99-106)."""
+
+
+class Tile(C.Structure):
+    """mb_tile (include/mandelbrot_b200.h): a sub-rectangle of one DataChunk's pixel grid."""
+    _fields_ = [
+        ("start_r", C.c_double), ("start_i", C.c_double),
+        ("stop_r", C.c_double), ("stop_i", C.c_double),
+        ("step_r", C.c_double), ("step_i", C.c_double),
+        ("definition", C.c_uint32), ("mrd", C.c_uint32),
+        ("x0", C.c_uint32), ("y0", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32),
+        ("out_offset", C.c_uint64),
+        ("out_pitch", C.c_uint32), ("flags", C.c_uint32),
+    ]
+
+    def copy(self) -> "Tile":
+        t = Tile()
+        C.memmove(C.byref(t), C.byref(self), C.sizeof(Tile))
+        return t
+
+    def sub(self, x0: int, y0: int, w: int, h: int, out_offset: int, out_pitch: int | None = None) -> "Tile":
+        """Sub-rectangle of this (whole-chunk) tile; indexes the same chunk-level linspace."""
+        t = self.copy()
+        t.x0, t.y0, t.w, t.h = x0, y0, w, h
+        t.out_offset = out_offset
+        t.out_pitch = w if out_pitch is None else out_pitch
+        return t
+
+
+assert C.sizeof(Tile) == 88
+
+_lib = None
+_lock = threading.Lock()
+
+# name -> (restype, argtypes); every symbol include/mandelbrot_b200.h declares
+_u32, _i32, _u64, _sz, _vp, _int = C.c_uint32, C.c_int32, C.c_uint64, C.c_size_t, C.c_void_p, C.c_int
+_PT = C.POINTER(Tile)
+SIGNATURES = {
+    "mb_init": (_int, [_int]),
+    "mb_shutdown": (None, []),
+    "mb_last_error": (C.c_char_p, []),
+    "mb_abi_version": (_int, []),
+    "mb_device_count": (_int, []),
+    "mb_sm_count": (_int, []),
+    "mb_chunk_geometry": (_int, [_u32, _u32, _u32, _u32, _u32, _PT]),
+    "mb_tile_coord": (C.c_double, [_PT, _int, _u32]),
+    "mb_render_counts": (_int, [_PT, _u32, _vp, _int, _vp]),
+    "mb_calc_mb_value_dev": (_int, [_vp, _vp, _sz, _u32, _int, _vp, _vp]),
+    "mb_calc_mb_value": (_int, [_vp, _vp, _sz, _u32, _int, _vp]),
+    "mb_render_u8": (_int, [_PT, _u32, _vp, _int, _vp]),
+    "mb_counts_to_u8": (_int, [_vp, _vp, _sz, _u32, _vp]),
+    "mb_useful_iterations": (_int, [_vp, _sz, _u32, _vp, _vp]),
+    "mb_classify_u8": (_int, [_vp, _sz, _vp, _vp]),
+    "mb_process_workload_u8": (_int, [_u32, _u32, _u32, _u32, _u32, _vp]),
+    "mb_process_workload_counts": (_int, [_u32, _u32, _u32, _u32, _u32, _int, _vp]),
+    "mb_wsq_create": (_int, [C.c_char_p, _u32, _u32, C.POINTER(_vp)]),
+    "mb_wsq_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
+    "mb_wsq_reset": (_int, [_vp, _u32]),
+    "mb_wsq_pop": (_int, [_vp, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "mb_wsq_close": (_int, [_vp]),
+    "mb_wsq_unlink": (_int, [C.c_char_p]),
+    "mb_measure_fma_peak": (_int, [_int, _int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "mb_measure_pipe_rate": (_int, [_int, _int, _int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+}
+
+
+def library_path() -> str:
+    return _build.SO
+
+
+def lib() -> C.CDLL:
+    """Load (building first if needed) the shared library and declare every signature."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(_build.SO):
+                _build.build()
+            L = C.CDLL(_build.SO)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)   # AttributeError here = header/library mismatch: fail loudly
+                fn.restype = res
+                fn.argtypes = args
+            if L.mb_abi_version() != 1:
+                raise NativeError(MB_ERR_STATE, "ABI version mismatch")
+            _lib = L
+    return _lib
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = lib().mb_last_error().decode("utf-8", "replace")
+        raise (InvalidArgument if rc == MB_ERR_INVALID else NativeError)(rc, msg)
+    return rc
+
+
+_inited = threading.local()
+
+
+def init(device: int = 0) -> None:
+    """mb_init: bind the calling thread to `device`.  Raises NativeError without a CUDA device."""
+    check(lib().mb_init(int(device)))
+    _inited.device = int(device)
+
+
+def ensure_init(device: int | None = None) -> int:
+    cur = getattr(_inited, "device", None)
+    if device is None:
+        device = cur if cur is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    if cur != device:
+        init(device)
+    return device
+
+
+def chunk_geometry(level: int, index_real: int, index_imag: int, definition: int = CHUNK_DEFINITION,
+                   mrd: int = 0) -> Tile:
+    """Whole-chunk tile descriptor (.py:75-78 + linspace parameters of .py:24-32).  Host only."""
+    for name, v in (("level", level), ("index_real", index_real), ("index_imag", index_imag),
+                    ("definition", definition), ("mrd", mrd)):
+        if not (0 <= int(v) <= 0xFFFFFFFF):
+            raise InvalidArgument(MB_ERR_INVALID, f"{name}={v} is not a uint32")
+    t = Tile()
+    check(lib().mb_chunk_geometry(int(level), int(index_real), int(index_imag), int(definition), int(mrd), C.byref(t)))
+    return t
+
+
+def tile_array(tiles) -> C.Array:
+    arr = (Tile * len(tiles))()
+    for k, t in enumerate(tiles):
+        C.memmove(C.byref(arr, k * C.sizeof(Tile)), C.byref(t), C.sizeof(Tile))
+    return arr
+
+
+def measure_pipe_rate(dtype="f64", mode: int = 0, iters: int = 4096):
+    """(tera lane-ops/s, ms) of the FMA pipe on the bound device (roofline denominator)."""
+    ensure_init()
+    rate, ms = C.c_double(), C.c_float()
+    check(lib().mb_measure_pipe_rate(DTYPES[dtype], mode, iters, C.byref(rate), C.byref(ms)))
+    return rate.value, ms.value
+
+
+class TileQueue:
+    """mb_wsq: work-stealing tile-index ranges shared by the GPU processes of one box.
+
+    In-box replacement for the Distributer's lease dispatch (Distributer.cs:335-392)."""
+
+    def __init__(self, name: str, n_ranks: int | None = None, total: int | None = None, create: bool = False):
+        self.name = name.encode()
+        self._h = _vp()
+        self._owner = create
+        if create:
+            check(lib().mb_wsq_create(self.name, n_ranks, total, C.byref(self._h)))
+        else:
+            check(lib().mb_wsq_open(self.name, C.byref(self._h)))
+
+    def reset(self, total: int) -> None:
+        check(lib().mb_wsq_reset(self._h, total))
+
+    def pop(self, rank: int, want: int = 1):
+        """-> (first, got, stolen) or None when the queue is drained."""
+        first, got, stolen = _u32(), _u32(), _u32()
+        rc = check(lib().mb_wsq_pop(self._h, rank, want, C.byref(first), C.byref(got), C.byref(stolen)))
+        if rc == 0:
+            return None
+        return first.value, got.value, bool(stolen.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().mb_wsq_close(self._h)
+            self._h = _vp()
+            if self._owner:
+                lib().mb_wsq_unlink(self.name)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

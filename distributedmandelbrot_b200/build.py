@@ -1,0 +1,58 @@
+"""Builds the in-tree C-ABI shared library with nvcc for sm_100a (no JIT cache: the .so must
+travel with the tree).  `python -m distributedmandelbrot_b200.build [--force]`."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+SO = os.path.join(PKG, "libmandelbrot_b200.so")
+SOURCES = ["mandelbrot_capi.cu", "tile_wsq.cpp"]
+HEADERS = ["escape_kernels.cuh", os.path.join("..", "..", "include", "mandelbrot_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                      # never contract a*b+c (parity; the kernels also use *_rn intrinsics)
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall",
+    "-shared", "-cudart", "shared",
+]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not (force or stale()):
+        return SO
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lrt"]
+    env = dict(os.environ)
+    env.pop("CC", None)   # $CC in this image points at a wrapper gcc nvcc must not pick up
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv))

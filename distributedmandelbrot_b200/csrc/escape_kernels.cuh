@@ -1,0 +1,299 @@
+// escape_kernels.cuh -- sm_100a device code of the escape-time hot path.
+//
+// Replaces the numba-generated `__vectorized_calc_mb_value` kernel of the reference worker
+// (DistributedMandelbrotWorkerCUDA/DistributedMandelbrotWorkerCUDA.py:39-68, launched at :92)
+// together with the host-side coordinate expansion gen_arrays (.py:19-37) and the host-side
+// uint8 scaling (.py:96-98).  Written from scratch; nothing here is derived from numba's PTX.
+//
+// Numerics contract: IEEE-754, round-to-nearest-even, every
+// operation individually rounded, in the order Python parses .py:50-62.  The reference's own
+// GPU build is FMA-contracted by libNVVM and therefore toolchain dependent; this kernel uses
+// only *_rn intrinsics (which nvcc never contracts) and the TU is compiled with -fmad=false.
+//
+// Per pixel-iteration the rounding sequence needs 7 FP64-pipe instructions:
+//     t  = x*y            DMUL
+//     a  = xx - yy        DADD      (xx = fl(x*x), yy = fl(y*y) carried from the magnitude test)
+//     y' = fma(t, 2, ci)  DFMA      == fl(fl((2x)*y) + ci): scaling by 2 is exact (no reachable
+//                                      subnormal: |ci| is 0 or >~1e-20)
+//     x' = a + cr         DADD
+//     xx = x'*x'          DMUL
+//     yy = y'*y'          DMUL
+//     m  = xx + yy        DADD
+// and the test m >= 4 is an integer compare of m's high word (m is finite and >= 0 before
+// escape), which issues on the ALU pipe in the FP64 pipe's shadow.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mandelbrot_b200.h"
+
+namespace mbk {
+
+constexpr int kWarpW = 8;   // a warp owns an 8 x 4 pixel patch: compact patches keep the lanes'
+constexpr int kWarpH = 4;   // escape times coherent near the set boundary (row-major 32x1 is worst)
+constexpr unsigned kFull = 0xffffffffu;
+
+template <typename Real> struct Ops;
+
+template <> struct Ops<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    // fl(2*t + c): one rounding; bit-identical to fl(fl((2x)*y) + c) with t = fl(x*y)
+    static __device__ __forceinline__ double twice_plus(double t, double c) { return __fma_rn(t, 2.0, c); }
+    // m >= 4.0 for finite m >= 0  <=>  hi32(m) >= hi32(4.0)
+    static __device__ __forceinline__ bool escaped(double m) { return __double2hiint(m) >= 0x40100000; }
+    static __device__ __forceinline__ double coord(double v) { return v; }
+};
+
+template <> struct Ops<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float twice_plus(float t, float c) { return __fmaf_rn(t, 2.0f, c); }
+    static __device__ __forceinline__ bool escaped(float m) { return __float_as_int(m) >= 0x40800000; }
+    // Appendix A.5: the binary64 linspace value rounded once to binary32
+    static __device__ __forceinline__ float coord(double v) { return __double2float_rn(v); }
+};
+
+// One pixel per lane.  `left` (= mrd-1 updates allowed) is uniform over a tile, so the
+// block structure below is warp-uniform: U updates with only the escape test between them,
+// then one warp vote; the whole warp leaves as soon as every lane has escaped or hit mrd.
+template <typename Real, int U>
+__device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool active)
+{
+    using O = Ops<Real>;
+    Real x = cr, y = ci;                       // z0 = c  (.py:44-45)
+    Real xx = O::mul(x, x), yy = O::mul(y, y);
+    int left = mrd - 1;                        // updates still allowed: n = 1 .. mrd-1 (.py:47)
+    int n = 0;                                 // updates performed
+    int result = 0;                            // 0 = never escaped (.py:68)
+    bool done = !active || left <= 0;
+    for (;;) {
+        if (!done) {
+            if (left >= U) {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const Real t = O::mul(x, y);
+                    const Real a = O::sub(xx, yy);
+                    y = O::twice_plus(t, ci);
+                    x = O::add(a, cr);
+                    xx = O::mul(x, x);
+                    yy = O::mul(y, y);
+                    const Real m = O::add(xx, yy);
+                    if (O::escaped(m)) { result = n + j + 1; done = true; break; }
+                }
+                n += U;
+                left -= U;
+                done = done || (left == 0);
+            } else {
+                for (; left > 0; --left) {
+                    const Real t = O::mul(x, y);
+                    const Real a = O::sub(xx, yy);
+                    y = O::twice_plus(t, ci);
+                    x = O::add(a, cr);
+                    xx = O::mul(x, x);
+                    yy = O::mul(y, y);
+                    const Real m = O::add(xx, yy);
+                    ++n;
+                    if (O::escaped(m)) { result = n; break; }
+                }
+                done = true;
+            }
+        }
+        if (__all_sync(kFull, done)) break;    // warp-vote early-out
+    }
+    return result;
+}
+
+// uint8 scaling of .py:96-98 in integers: ceil(n*256/mrd) mod 256
+__device__ __forceinline__ uint32_t count_to_u8(uint32_t n, uint32_t mrd)
+{
+    if (mrd <= (1u << 23)) return ((n * 256u + mrd - 1u) / mrd) & 0xffu;
+    return (uint32_t)((((uint64_t)n << 8) + mrd - 1u) / mrd) & 0xffu;
+}
+
+// Tile-axis sample k of the chunk-level linspace (numpy rounding sequence, .py:24-32)
+__device__ __forceinline__ double linspace_at(uint32_t k, uint32_t d_minus_1, double start, double step, double stop)
+{
+    return (k == d_minus_1) ? stop : __dadd_rn(__dmul_rn((double)k, step), start);
+}
+
+// CTA = WX x WY warps; each warp an 8x4 patch.  grid.x = CTAs per tile (row-major over the
+// tile), grid.y = tile index.  OutT = int32_t (counts) or uint8_t (fused .py:96-98 epilogue).
+template <typename Real, typename OutT, int U, int WX, int WY, int MIN_CTAS>
+__global__ void __launch_bounds__(WX * WY * 32, MIN_CTAS)
+escape_tiles_kernel(const mb_tile *__restrict__ tiles, OutT *__restrict__ out)
+{
+    // shared-memory staging of this CTA's tile descriptor (its complex-plane bounds)
+    __shared__ mb_tile s_tile;
+    static_assert(sizeof(mb_tile) % 8 == 0, "descriptor is copied as 64-bit words");
+    if (threadIdx.x < sizeof(mb_tile) / 8)
+        reinterpret_cast<uint64_t *>(&s_tile)[threadIdx.x] =
+            reinterpret_cast<const uint64_t *>(tiles + blockIdx.y)[threadIdx.x];
+    __syncthreads();
+
+    constexpr uint32_t CW = WX * kWarpW, CH = WY * kWarpH;
+    const uint32_t w = s_tile.w, h = s_tile.h;
+    const uint32_t nbx = (w + CW - 1) / CW, nby = (h + CH - 1) / CH;
+    if (blockIdx.x >= nbx * nby) return;       // grid.x is the max over the launch's tiles
+    const uint32_t by = blockIdx.x / nbx, bx = blockIdx.x - by * nbx;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t px = bx * CW + (warp % WX) * kWarpW + (lane & 7);
+    const uint32_t py = by * CH + (warp / WX) * kWarpH + (lane >> 3);
+    const bool active = (px < w) && (py < h);
+
+    const uint32_t d1 = s_tile.definition - 1u;
+    const double cr64 = linspace_at(s_tile.x0 + px, d1, s_tile.start_r, s_tile.step_r, s_tile.stop_r);
+    const double ci64 = linspace_at(s_tile.y0 + py, d1, s_tile.start_i, s_tile.step_i, s_tile.stop_i);
+    const uint32_t mrd = s_tile.mrd;
+
+    const int res = escape_count<Real, U>(Ops<Real>::coord(cr64), Ops<Real>::coord(ci64), (int)mrd, active);
+
+    const size_t row_off = s_tile.out_offset + (size_t)py * s_tile.out_pitch;
+    if constexpr (sizeof(OutT) == 4) {
+        // 128-bit stores: lanes 0 and 4 of each patch row write 4 consecutive counts
+        const int v1 = __shfl_down_sync(kFull, res, 1);
+        const int v2 = __shfl_down_sync(kFull, res, 2);
+        const int v3 = __shfl_down_sync(kFull, res, 3);
+        const uint32_t gpx = px & ~3u;         // patches are 8-aligned in tile space
+        int32_t *gp = reinterpret_cast<int32_t *>(out) + row_off + gpx;
+        const bool vec = (gpx + 3u < w) && (py < h) && ((reinterpret_cast<uintptr_t>(gp) & 15u) == 0);
+        if (vec) {
+            if ((lane & 3u) == 0) *reinterpret_cast<int4 *>(gp) = make_int4(res, v1, v2, v3);
+        } else if (active) {
+            reinterpret_cast<int32_t *>(out)[row_off + px] = res;
+        }
+    } else {
+        // fused uint8 epilogue; one 64-bit store per patch row
+        const uint32_t b = count_to_u8((uint32_t)res, mrd);
+        uint32_t v = b | (__shfl_down_sync(kFull, b, 1) << 8);
+        v |= __shfl_down_sync(kFull, v, 2) << 16;
+        const uint32_t hi = __shfl_down_sync(kFull, v, 4);
+        const uint32_t gpx = px & ~7u;
+        uint8_t *gp = reinterpret_cast<uint8_t *>(out) + row_off + gpx;
+        const bool vec = (gpx + 7u < w) && (py < h) && ((reinterpret_cast<uintptr_t>(gp) & 7u) == 0);
+        if (vec) {
+            if ((lane & 7u) == 0) *reinterpret_cast<uint2 *>(gp) = make_uint2(v, hi);
+        } else if (active) {
+            reinterpret_cast<uint8_t *>(out)[row_off + px] = (uint8_t)b;
+        }
+    }
+}
+
+// calc_mb_value as the reference exposes it (.py:39-42,92): explicit coordinate arrays, one
+// thread per element, 32 consecutive elements per warp (the caller chose the order).
+template <typename Real, int U>
+__global__ void __launch_bounds__(128, 16)
+escape_points_kernel(const double *__restrict__ r, const double *__restrict__ i, size_t n, int mrd, int32_t *__restrict__ out)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = k < n;
+    const double cr = active ? r[k] : 0.0, ci = active ? i[k] : 0.0;
+    const int res = escape_count<Real, U>(Ops<Real>::coord(cr), Ops<Real>::coord(ci), mrd, active);
+    if (active) out[k] = res;
+}
+
+// ---- small HBM-bound helpers ---------------------------------------------------------------
+
+// .py:96-98 over a flat int32 array
+__global__ void counts_to_u8_kernel(const int32_t *__restrict__ counts, uint8_t *__restrict__ out, size_t n, uint32_t mrd)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(counts) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (aligned) {
+        for (size_t k = i; k < n4; k += stride) {
+            const int4 c = reinterpret_cast<const int4 *>(counts)[k];
+            const uint32_t p = count_to_u8(c.x, mrd) | (count_to_u8(c.y, mrd) << 8) |
+                               (count_to_u8(c.z, mrd) << 16) | (count_to_u8(c.w, mrd) << 24);
+            reinterpret_cast<uint32_t *>(out)[k] = p;
+        }
+        for (size_t k = n4 * 4 + i; k < n; k += stride) out[k] = (uint8_t)count_to_u8(counts[k], mrd);
+    } else {
+        for (size_t k = i; k < n; k += stride) out[k] = (uint8_t)count_to_u8(counts[k], mrd);
+    }
+}
+
+// sum of (n ? n : mrd-1): the pixel-iterations the reference semantics require
+__global__ void useful_iterations_kernel(const int32_t *__restrict__ counts, size_t n, uint32_t mrd, unsigned long long *sum)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned long long never = mrd ? mrd - 1u : 0u;
+    unsigned long long acc = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int c = counts[k];
+        acc += c ? (unsigned long long)c : never;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(kFull, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum, acc);
+}
+
+// DataChunk.IsNeverChunk / IsImmediateChunk (DataChunk.cs:82,87): flags start at {1,1}
+__global__ void classify_u8_kernel(const uint8_t *__restrict__ p, size_t n, uint32_t *flags)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool all0 = true, all1 = true;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint8_t v = p[k];
+        all0 = all0 && (v == 0);
+        all1 = all1 && (v == 1);
+    }
+    if (!__all_sync(kFull, all0) && (threadIdx.x & 31) == 0) flags[0] = 0;
+    if (!__all_sync(kFull, all1) && (threadIdx.x & 31) == 0) flags[1] = 0;
+}
+
+// ---- roofline denominator microbenchmarks ----------------------------------------------------
+// mode 0: CHAINS independent FMA chains per thread, nothing else (pure pipe issue rate)
+// mode 1: the 7-op Mandelbrot update without the escape test (arithmetic ceiling of the loop)
+template <typename Real, int CHAINS>
+__global__ void __launch_bounds__(256) fma_peak_kernel(Real *sink, int iters, Real seed)
+{
+    Real a[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) a[c] = seed + (Real)(threadIdx.x + c);
+    const Real m = (Real)0.999999, b = (Real)1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < CHAINS; ++c) {
+                if constexpr (sizeof(Real) == 8) a[c] = __fma_rn(a[c], m, b);
+                else a[c] = __fmaf_rn(a[c], m, b);
+            }
+    }
+    Real s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += a[c];
+    if (s == (Real)123.456) sink[0] = s;    // never true; keeps the chains alive
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) mandel_mix_kernel(Real *sink, int iters, Real seed)
+{
+    using O = Ops<Real>;
+    // bounded orbits (period-2 bulb / cardioid interior) so values stay finite
+    const Real cr = (Real)-0.1 + seed * (Real)(threadIdx.x & 31) * (Real)1e-3;
+    const Real ci = (Real)0.05 + seed * (Real)(threadIdx.x >> 5) * (Real)1e-3;
+    Real x = cr, y = ci, xx = O::mul(x, x), yy = O::mul(y, y);
+    int bits = 0;   // keeps every magnitude add alive at the cost of one ALU-pipe LOP3
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const Real t = O::mul(x, y);
+            const Real a = O::sub(xx, yy);
+            y = O::twice_plus(t, ci);
+            x = O::add(a, cr);
+            xx = O::mul(x, x);
+            yy = O::mul(y, y);
+            const Real m = O::add(xx, yy);
+            if constexpr (sizeof(Real) == 8) bits |= __double2hiint(m);
+            else bits |= __float_as_int(m);
+        }
+    }
+    if (bits == 0x7fffffff) sink[0] = x;
+}
+
+}  // namespace mbk

@@ -1,0 +1,438 @@
+// mandelbrot_capi.cu -- implementation of include/mandelbrot_b200.h (the C-ABI boundary).
+//
+// Host side of the hot path: argument checking in the spirit of the DataChunk ctor
+// (DistributedMandelbrot/DataChunk.cs:99-106), chunk geometry (.py:75-78 / DataChunk.cs:32-33,
+// 59-66), linspace parameters (.py:24-32), kernel launches, and the synchronous
+// process_workload equivalents (.py:70-100).  No CPU compute fallback exists in this file:
+// every compute entry point either launches a CUDA kernel or fails.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "escape_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_device = -1;
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MB_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(MB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+constexpr int kMaxDevices = 64;
+
+// per-device context for the synchronous process_workload path
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;      // private non-blocking stream for the host-buffer entry points
+    void *scratch = nullptr;            // device output buffer of the host-buffer entry points
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+};
+DeviceCtx g_ctx[kMaxDevices];
+
+int current_ctx(DeviceCtx **out)
+{
+    if (g_device < 0 || g_device >= kMaxDevices || !g_ctx[g_device].ready)
+        return fail(MB_ERR_STATE, "mb_init(device) has not been called on this thread");
+    MB_CUDA(cudaSetDevice(g_device));
+    *out = &g_ctx[g_device];
+    return MB_OK;
+}
+
+int ensure_scratch(DeviceCtx *c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return MB_OK;
+    if (c->scratch) {
+        MB_CUDA(cudaFree(c->scratch));
+        c->scratch = nullptr;
+        c->scratch_bytes = 0;
+    }
+    MB_CUDA(cudaMalloc(&c->scratch, bytes));
+    c->scratch_bytes = bytes;
+    return MB_OK;
+}
+
+int check_tiles(const mb_tile *tiles, uint32_t n_tiles, uint32_t *max_w, uint32_t *max_h)
+{
+    if (!tiles || n_tiles == 0) return fail(MB_ERR_INVALID, "no tiles");
+    uint32_t mw = 0, mh = 0;
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+        const mb_tile &t = tiles[k];
+        if (t.definition == 0) return fail(MB_ERR_INVALID, "tile %u: definition == 0", k);
+        if (t.w == 0 || t.h == 0) return fail(MB_ERR_INVALID, "tile %u: empty rectangle", k);
+        if ((uint64_t)t.x0 + t.w > t.definition || (uint64_t)t.y0 + t.h > t.definition)
+            return fail(MB_ERR_INVALID, "tile %u: rectangle exceeds the chunk grid", k);
+        if (t.mrd > 0x7fffffffu) return fail(MB_ERR_INVALID, "tile %u: mrd exceeds int32 (.py:39)", k);
+        if (t.out_pitch < t.w) return fail(MB_ERR_INVALID, "tile %u: out_pitch < w", k);
+        if (t.flags != 0) return fail(MB_ERR_INVALID, "tile %u: flags must be 0", k);
+        mw = t.w > mw ? t.w : mw;
+        mh = t.h > mh ? t.h : mh;
+    }
+    *max_w = mw;
+    *max_h = mh;
+    return MB_OK;
+}
+
+// Launch shape.  CTA = 2 x 2 warps of 8x4 pixels (16 x 8 pixels, 128 threads): small CTAs
+// release their SM slots soon after their own pixels finish, which matters because escape
+// times differ by orders of magnitude between neighbouring CTAs at the set boundary.
+// <= 32 registers/thread and 16 CTAs/SM = 64 resident warps/SM (full occupancy on sm_100).
+constexpr int kWX = 2, kWY = 2, kMinCtas = 16, kUnroll = 8;
+constexpr uint32_t kCtaW = kWX * mbk::kWarpW, kCtaH = kWY * mbk::kWarpH;
+constexpr uint32_t kMaxGridY = 65535;
+
+template <typename OutT>
+int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtype, cudaStream_t st)
+{
+    uint32_t mw = 0, mh = 0;
+    int rc = check_tiles(tiles, n_tiles, &mw, &mh);
+    if (rc) return rc;
+    if (!out_dev) return fail(MB_ERR_INVALID, "out_dev is NULL");
+    if (dtype != MB_DTYPE_F64 && dtype != MB_DTYPE_F32) return fail(MB_ERR_INVALID, "unknown dtype %d", dtype);
+    DeviceCtx *c = nullptr;
+    if ((rc = current_ctx(&c))) return rc;
+
+    // descriptors travel as a stream-ordered device allocation: 88 bytes per tile is the whole
+    // input of the hot path (the reference ships 2 x 128 MiB of float64 per chunk, .py:82-88)
+    mb_tile *tiles_dev = nullptr;
+    const size_t bytes = sizeof(mb_tile) * (size_t)n_tiles;
+    MB_CUDA(cudaMallocAsync((void **)&tiles_dev, bytes, st));
+    MB_CUDA(cudaMemcpyAsync(tiles_dev, tiles, bytes, cudaMemcpyHostToDevice, st));
+
+    const uint32_t ctas_per_tile = ((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
+    for (uint32_t first = 0; first < n_tiles; first += kMaxGridY) {
+        const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
+        const dim3 grid(ctas_per_tile, cnt, 1), block(kWX * kWY * 32, 1, 1);
+        if (dtype == MB_DTYPE_F64)
+            mbk::escape_tiles_kernel<double, OutT, kUnroll, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(tiles_dev + first, out_dev);
+        else
+            mbk::escape_tiles_kernel<float, OutT, kUnroll, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(tiles_dev + first, out_dev);
+        MB_CUDA(cudaGetLastError());
+    }
+    MB_CUDA(cudaFreeAsync(tiles_dev, st));
+    return MB_OK;
+}
+
+// strict binary64 host arithmetic: `volatile` pins each rounding even if someone adds -mfma
+inline double f_mul(double a, double b) { volatile double r = a * b; return r; }
+inline double f_add(double a, double b) { volatile double r = a + b; return r; }
+inline double f_sub(double a, double b) { volatile double r = a - b; return r; }
+inline double f_div(double a, double b) { volatile double r = a / b; return r; }
+
+int grid_for(size_t n, int sm_count)
+{
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+// shared with tile_wsq.cpp so that queue errors are readable through mb_last_error()
+int mb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
+
+int mb_abi_version(void) { return MB_ABI_VERSION; }
+
+const char *mb_last_error(void) { return g_err; }
+
+int mb_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(MB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int mb_init(int device)
+{
+    if (device < 0 || device >= kMaxDevices) return fail(MB_ERR_INVALID, "device %d out of range", device);
+    int n = mb_device_count();
+    if (n < 0) return n;
+    if (device >= n) return fail(MB_ERR_CUDA, "device %d requested but only %d CUDA device(s) present", device, n);
+    MB_CUDA(cudaSetDevice(device));
+    DeviceCtx &c = g_ctx[device];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) {
+        cudaDeviceProp prop;
+        MB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(MB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        c.sm_count = prop.multiProcessorCount;
+        MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.ready = true;
+    }
+    g_device = device;
+    return MB_OK;
+}
+
+void mb_shutdown(void)
+{
+    for (int d = 0; d < kMaxDevices; ++d) {
+        DeviceCtx &c = g_ctx[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (!c.ready) continue;
+        cudaSetDevice(d);
+        if (c.scratch) cudaFree(c.scratch);
+        if (c.stream) cudaStreamDestroy(c.stream);
+        c.scratch = nullptr;
+        c.scratch_bytes = 0;
+        c.stream = nullptr;
+        c.ready = false;
+    }
+    g_device = -1;
+}
+
+int mb_sm_count(void)
+{
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    return rc ? rc : c->sm_count;
+}
+
+int mb_chunk_geometry(uint32_t level, uint32_t index_real, uint32_t index_imag, uint32_t definition,
+                      uint32_t mrd, mb_tile *out)
+{
+    if (!out) return fail(MB_ERR_INVALID, "out is NULL");
+    // DataChunk.cs:99-106
+    if (level == 0) return fail(MB_ERR_INVALID, "Level must be positive");
+    if (index_real >= level) return fail(MB_ERR_INVALID, "Real index must be lesser than level");
+    if (index_imag >= level) return fail(MB_ERR_INVALID, "Imag index must be lesser than level");
+    if (definition == 0) return fail(MB_ERR_INVALID, "definition must be >= 1");
+    if (mrd > 0x7fffffffu) return fail(MB_ERR_INVALID, "mrd exceeds int32 (.py:39)");
+    // .py:75-78
+    const double range = f_div(f_sub(MB_MAX_AXIS, MB_MIN_AXIS), (double)level);
+    const double start_r = f_add(MB_MIN_AXIS, f_mul(range, (double)index_real));
+    const double start_i = f_add(MB_MIN_AXIS, f_mul(range, (double)index_imag));
+    std::memset(out, 0, sizeof(*out));
+    out->start_r = start_r;
+    out->start_i = start_i;
+    if (definition > 1) {
+        // .py:24-32 -> numpy.linspace: stop = start + _range ; step = (stop - start) / (num - 1)
+        out->stop_r = f_add(start_r, range);
+        out->stop_i = f_add(start_i, range);
+        out->step_r = f_div(f_sub(out->stop_r, start_r), (double)(definition - 1));
+        out->step_i = f_div(f_sub(out->stop_i, start_i), (double)(definition - 1));
+    } else {
+        // numpy.linspace(num=1) is [start]: the forced-endpoint slot (k == definition-1 == 0) holds start
+        out->stop_r = start_r;
+        out->stop_i = start_i;
+        out->step_r = 0.0;
+        out->step_i = 0.0;
+    }
+    out->definition = definition;
+    out->mrd = mrd;
+    out->x0 = out->y0 = 0;
+    out->w = out->h = definition;
+    out->out_offset = 0;
+    out->out_pitch = definition;
+    out->flags = 0;
+    return MB_OK;
+}
+
+double mb_tile_coord(const mb_tile *t, int axis, uint32_t k)
+{
+    const double start = axis ? t->start_i : t->start_r;
+    const double step = axis ? t->step_i : t->step_r;
+    const double stop = axis ? t->stop_i : t->stop_r;
+    if (k == t->definition - 1u) return stop;
+    return f_add(f_mul((double)k, step), start);
+}
+
+int mb_render_counts(const mb_tile *tiles, uint32_t n_tiles, int32_t *out_dev, int dtype, void *stream)
+{
+    return launch_tiles<int32_t>(tiles, n_tiles, out_dev, dtype, (cudaStream_t)stream);
+}
+
+int mb_calc_mb_value_dev(const double *r_dev, const double *i_dev, size_t n, uint32_t mrd, int dtype,
+                         int32_t *out_dev, void *stream)
+{
+    if (!r_dev || !i_dev || !out_dev) return fail(MB_ERR_INVALID, "NULL buffer");
+    if (mrd > 0x7fffffffu) return fail(MB_ERR_INVALID, "mrd exceeds int32 (.py:39)");
+    if (dtype != MB_DTYPE_F64 && dtype != MB_DTYPE_F32) return fail(MB_ERR_INVALID, "unknown dtype %d", dtype);
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    if (n == 0) return MB_OK;
+    const size_t blocks = (n + 127) / 128;
+    if (blocks > 0x7fffffffull) return fail(MB_ERR_INVALID, "too many elements for one launch");
+    if (dtype == MB_DTYPE_F64)
+        mbk::escape_points_kernel<double, kUnroll><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(r_dev, i_dev, n, (int)mrd, out_dev);
+    else
+        mbk::escape_points_kernel<float, kUnroll><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(r_dev, i_dev, n, (int)mrd, out_dev);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int mb_calc_mb_value(const double *r_host, const double *i_host, size_t n, uint32_t mrd, int dtype, int32_t *out_host)
+{
+    if (!r_host || !i_host || !out_host) return fail(MB_ERR_INVALID, "NULL buffer");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    if (n == 0) return MB_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    // layout of the scratch buffer: r[n] | i[n] | out[n]
+    if ((rc = ensure_scratch(c, n * (2 * sizeof(double) + sizeof(int32_t))))) return rc;
+    double *r_dev = static_cast<double *>(c->scratch);
+    double *i_dev = r_dev + n;
+    int32_t *o_dev = reinterpret_cast<int32_t *>(i_dev + n);
+    MB_CUDA(cudaMemcpyAsync(r_dev, r_host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(cudaMemcpyAsync(i_dev, i_host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = mb_calc_mb_value_dev(r_dev, i_dev, n, mrd, dtype, o_dev, c->stream))) return rc;
+    MB_CUDA(cudaMemcpyAsync(out_host, o_dev, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+
+int mb_render_u8(const mb_tile *tiles, uint32_t n_tiles, uint8_t *out_dev, int dtype, void *stream)
+{
+    for (uint32_t k = 0; tiles && k < n_tiles; ++k)
+        if (tiles[k].mrd == 0) return fail(MB_ERR_INVALID, "tile %u: mrd == 0 divides by zero in the uint8 scaling (.py:96)", k);
+    return launch_tiles<uint8_t>(tiles, n_tiles, out_dev, dtype, (cudaStream_t)stream);
+}
+
+int mb_counts_to_u8(const int32_t *counts_dev, uint8_t *out_dev, size_t n, uint32_t mrd, void *stream)
+{
+    if (!counts_dev || !out_dev) return fail(MB_ERR_INVALID, "NULL buffer");
+    if (mrd == 0) return fail(MB_ERR_INVALID, "mrd == 0 divides by zero in the uint8 scaling (.py:96)");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    if (n == 0) return MB_OK;
+    mbk::counts_to_u8_kernel<<<grid_for((n + 3) / 4, c->sm_count), 256, 0, (cudaStream_t)stream>>>(counts_dev, out_dev, n, mrd);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int mb_useful_iterations(const int32_t *counts_dev, size_t n, uint32_t mrd, uint64_t *sum_dev, void *stream)
+{
+    if (!counts_dev || !sum_dev) return fail(MB_ERR_INVALID, "NULL buffer");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    if (n == 0) return MB_OK;
+    mbk::useful_iterations_kernel<<<grid_for(n, c->sm_count), 256, 0, (cudaStream_t)stream>>>(
+        counts_dev, n, mrd, reinterpret_cast<unsigned long long *>(sum_dev));
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int mb_classify_u8(const uint8_t *payload_dev, size_t n, uint32_t *flags_dev, void *stream)
+{
+    if (!payload_dev || !flags_dev) return fail(MB_ERR_INVALID, "NULL buffer");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    const uint32_t ones[2] = {1u, 1u};
+    MB_CUDA(cudaMemcpyAsync(flags_dev, ones, sizeof(ones), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (n == 0) return MB_OK;
+    mbk::classify_u8_kernel<<<grid_for(n, c->sm_count), 256, 0, (cudaStream_t)stream>>>(payload_dev, n, flags_dev);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int mb_process_workload_u8(uint32_t level, uint32_t mrd, uint32_t index_real, uint32_t index_imag,
+                           uint32_t definition, uint8_t *host_out)
+{
+    if (!host_out) return fail(MB_ERR_INVALID, "host_out is NULL");
+    mb_tile t;
+    int rc = mb_chunk_geometry(level, index_real, index_imag, definition, mrd, &t);
+    if (rc) return rc;
+    DeviceCtx *c = nullptr;
+    if ((rc = current_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = (size_t)definition * definition;
+    if ((rc = ensure_scratch(c, n))) return rc;
+    if ((rc = mb_render_u8(&t, 1, static_cast<uint8_t *>(c->scratch), MB_DTYPE_F64, c->stream))) return rc;
+    MB_CUDA(cudaMemcpyAsync(host_out, c->scratch, n, cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+
+int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real, uint32_t index_imag,
+                               uint32_t definition, int dtype, int32_t *host_out)
+{
+    if (!host_out) return fail(MB_ERR_INVALID, "host_out is NULL");
+    mb_tile t;
+    int rc = mb_chunk_geometry(level, index_real, index_imag, definition, mrd, &t);
+    if (rc) return rc;
+    DeviceCtx *c = nullptr;
+    if ((rc = current_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t bytes = (size_t)definition * definition * sizeof(int32_t);
+    if ((rc = ensure_scratch(c, bytes))) return rc;
+    if ((rc = mb_render_counts(&t, 1, static_cast<int32_t *>(c->scratch), dtype, c->stream))) return rc;
+    MB_CUDA(cudaMemcpyAsync(host_out, c->scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+
+int mb_measure_pipe_rate(int dtype, int mode, int iters, double *tera_ops_per_s, float *elapsed_ms)
+{
+    if (!tera_ops_per_s) return fail(MB_ERR_INVALID, "NULL result pointer");
+    if (iters <= 0) return fail(MB_ERR_INVALID, "iters must be positive");
+    if (dtype != MB_DTYPE_F64 && dtype != MB_DTYPE_F32) return fail(MB_ERR_INVALID, "unknown dtype %d", dtype);
+    if (mode != 0 && mode != 1) return fail(MB_ERR_INVALID, "unknown mode %d", mode);
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if ((rc = ensure_scratch(c, 64))) return rc;
+    constexpr int kChains = 8, kThreads = 256, kCtasPerSm = 8;
+    const int grid = c->sm_count * kCtasPerSm;
+    cudaEvent_t e0, e1;
+    MB_CUDA(cudaEventCreate(&e0));
+    MB_CUDA(cudaEventCreate(&e1));
+    float ms = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0 warms up
+        MB_CUDA(cudaEventRecord(e0, c->stream));
+        if (dtype == MB_DTYPE_F64) {
+            if (mode == 0) mbk::fma_peak_kernel<double, kChains><<<grid, kThreads, 0, c->stream>>>((double *)c->scratch, iters, 1.0);
+            else mbk::mandel_mix_kernel<double><<<grid, kThreads, 0, c->stream>>>((double *)c->scratch, iters, 1.0);
+        } else {
+            if (mode == 0) mbk::fma_peak_kernel<float, kChains><<<grid, kThreads, 0, c->stream>>>((float *)c->scratch, iters, 1.0f);
+            else mbk::mandel_mix_kernel<float><<<grid, kThreads, 0, c->stream>>>((float *)c->scratch, iters, 1.0f);
+        }
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaEventRecord(e1, c->stream));
+        MB_CUDA(cudaEventSynchronize(e1));
+        MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double per_thread = mode == 0 ? (double)kChains * 8.0 * iters : 7.0 * 8.0 * iters;
+    const double ops = per_thread * (double)kThreads * (double)grid;
+    *tera_ops_per_s = ops / ((double)ms * 1e-3) / 1e12;
+    if (elapsed_ms) *elapsed_ms = ms;
+    return MB_OK;
+}
+
+int mb_measure_fma_peak(int dtype, int iters, double *tera_fma_per_s, float *elapsed_ms)
+{
+    return mb_measure_pipe_rate(dtype, 0, iters, tera_fma_per_s, elapsed_ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""In-box frame renderer: a B x B block of DataChunks rendered on the GPUs of one box.
+
+A frame is what the reference's Distributer iterates over for one level setting
+(Distributer.TryGetNextNeededWorkload, Distributer.cs:335-353): chunks (level, indexReal,
+indexImag) with the same mrd.  Here the chunks of a frame are cut into row bands (the unit of
+dispatch), the bands are handed to one process per GPU by the shared-memory work-stealing queue
+(csrc/tile_wsq.cpp -- the in-box replacement for the socket dispatch), every band is rendered by
+the sm_100a escape-time kernel straight into its final position of a chunk-contiguous int32
+image, and ONE batched NCCL send/recv moves the bands to rank 0 (the only collective: pixels,
+hence bands, are independent -- no halo, no reduction).
+
+Output layout (also the wire/disk shape of the reference, one DataChunk after another):
+    image[chunk][row][col], chunk = bi * B + br  for chunk indices (ir0 + br, ii0 + bi),
+    row = imag index, col = real index inside the chunk (p = row*d + col, .py:34-35).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import os
+from typing import Callable, List, Optional, Sequence, Tuple
+
+from . import _native as nat
+
+
+@dataclasses.dataclass(frozen=True)
+class FrameSpec:
+    """B x B chunks at `level`, chunk indices [ir0, ir0+B) x [ii0, ii0+B)."""
+    name: str
+    level: int
+    blocks: int
+    definition: int
+    ir0: int
+    ii0: int
+    mrd: int
+    dtype: str = "f64"
+    band_rows: int = 256          # rows per dispatch unit (a band is contiguous in the chunk layout)
+
+    @property
+    def n_chunks(self) -> int:
+        return self.blocks * self.blocks
+
+    @property
+    def pixels(self) -> int:
+        return self.n_chunks * self.definition * self.definition
+
+    @property
+    def bands_per_chunk(self) -> int:
+        return (self.definition + self.band_rows - 1) // self.band_rows
+
+    @property
+    def n_bands(self) -> int:
+        return self.n_chunks * self.bands_per_chunk
+
+    def chunk_indices(self) -> List[Tuple[int, int]]:
+        return [(self.ir0 + br, self.ii0 + bi) for bi in range(self.blocks) for br in range(self.blocks)]
+
+    def scaled(self, **kw) -> "FrameSpec":
+        return dataclasses.replace(self, **kw)
+
+
+# BASELINE.json configs pinned to concrete inputs (BASELINE.md section 5 / SURVEY.md 8d)
+CONFIGS = {
+    "cfg1": FrameSpec("cfg1: single 512x512 DataChunk, mrd=256", 4, 1, 512, 1, 2, 256, "f64", 64),
+    "cfg2": FrameSpec("cfg2: 4096x4096 whole plane, mrd=1024, one 256x256 chunk per SM-sized tile", 16, 16, 256, 0, 0, 1024, "f64", 256),
+    "cfg3": FrameSpec("cfg3: 16384x16384 whole plane, mrd=4096, FP32", 4, 4, 4096, 0, 0, 4096, "f32", 256),
+    "cfg4": FrameSpec("cfg4: 65536x65536 zoom at -0.75+0.1i, mrd=10000", 800, 16, 4096, 242, 412, 10000, "f64", 256),
+    "cfg5": FrameSpec("cfg5: 32768x32768 seahorse zoom at -0.743643+0.131825i, mrd=50000", 4000000, 8, 4096, 1256353, 2131821, 50000, "f64", 64),
+}
+
+
+def frame_bands(spec: FrameSpec):
+    """ctypes array of band tiles in dispatch order + each band's (element offset, element count)."""
+    d = spec.definition
+    tiles, extents = [], []
+    for c, (ir, ii) in enumerate(spec.chunk_indices()):
+        chunk = nat.chunk_geometry(spec.level, ir, ii, d, spec.mrd)
+        for y0 in range(0, d, spec.band_rows):
+            h = min(spec.band_rows, d - y0)
+            off = c * d * d + y0 * d
+            tiles.append(chunk.sub(0, y0, d, h, off, d))
+            extents.append((off, h * d))
+    return nat.tile_array(tiles), extents
+
+
+def coalesce(ranges: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """Merge adjacent (first, count) band ranges."""
+    out: List[Tuple[int, int]] = []
+    for first, cnt in sorted(ranges):
+        if out and out[-1][0] + out[-1][1] == first:
+            out[-1] = (out[-1][0], out[-1][1] + cnt)
+        else:
+            out.append((first, cnt))
+    return out
+
+
+class FrameRenderer:
+    """Renders `spec` on this process's GPU (single GPU) or, with a TileQueue and a
+    torch.distributed process group, on all GPUs of the box with a final gather to rank 0."""
+
+    def __init__(self, spec: FrameSpec, device: int = 0, rank: int = 0, world: int = 1,
+                 launch: Optional[Callable] = None, out=None, bands_per_claim: int = 4, depth: int = 3):
+        import torch
+        self.torch = torch
+        self.spec, self.rank, self.world = spec, rank, world
+        self.tiles, self.extents = frame_bands(spec)
+        self.bands_per_claim, self.depth = bands_per_claim, depth
+        self._tile_size = C.sizeof(nat.Tile)
+        if launch is None:
+            nat.ensure_init(device)
+            self.device = torch.device("cuda", device)
+            self._launch = self._launch_cuda
+        else:                                   # test hook (CPU / gloo): launch(first, count, out)
+            self.device = torch.device("cpu")
+            self._launch = launch
+        self.out = out if out is not None else torch.empty(spec.pixels, dtype=torch.int32, device=self.device)
+        self.claimed: List[Tuple[int, int]] = []
+        self.steals = 0
+        self.launches = 0
+
+    # -- launching ---------------------------------------------------------------------------
+    def _launch_cuda(self, first: int, count: int, out) -> None:
+        torch = self.torch
+        ptr = C.cast(C.byref(self.tiles, first * self._tile_size), C.POINTER(nat.Tile))
+        nat.check(nat.lib().mb_render_counts(ptr, count, out.data_ptr(), nat.DTYPES[self.spec.dtype],
+                                             torch.cuda.current_stream(self.device).cuda_stream))
+
+    def render_all(self) -> None:
+        """Single GPU, no queue: every band in ONE launch (grid.y = band index)."""
+        self._launch(0, self.spec.n_bands, self.out)
+        self.claimed = [(0, self.spec.n_bands)]
+        self.launches += 1
+
+    def render_stolen(self, queue: "nat.TileQueue") -> None:
+        """Claim bands from the work-stealing queue until it is drained; at most `depth`
+        launches in flight so that ranks which run ahead cannot hoard the queue."""
+        torch = self.torch
+        self.claimed, self.steals = [], 0
+        inflight = []
+        cuda = self.device.type == "cuda"
+        while True:
+            got = queue.pop(self.rank, self.bands_per_claim)
+            if got is None:
+                break
+            first, cnt, stolen = got
+            self.steals += int(stolen)
+            self._launch(first, cnt, self.out)
+            self.launches += 1
+            self.claimed.append((first, cnt))
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                inflight.append(ev)
+                if len(inflight) >= self.depth:
+                    inflight.pop(0).synchronize()
+        self.claimed = coalesce(self.claimed)
+
+    # -- the one collective -------------------------------------------------------------------
+    def gather_to_root(self, group=None) -> None:
+        """All ranks learn who rendered what (tiny all_gather_object), then one batch of
+        point-to-point transfers places every band at its final offset on rank 0 (grouped
+        ncclSend/ncclRecv over NVLink; ownership is dynamic, so a fixed-shape gather would not fit)."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        owned = [None] * self.world
+        dist.all_gather_object(owned, self.claimed, group=group)
+        ops = []
+        for src in range(1, self.world):
+            for first, cnt in owned[src]:
+                lo = self.extents[first][0]
+                hi = self.extents[first + cnt - 1][0] + self.extents[first + cnt - 1][1]
+                view = self.out[lo:hi]
+                if self.rank == 0:
+                    ops.append(dist.P2POp(dist.irecv, view, src, group=group))
+                elif self.rank == src:
+                    ops.append(dist.P2POp(dist.isend, view, 0, group=group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    # -- metric -------------------------------------------------------------------------------
+    def useful_iterations(self) -> int:
+        """sum over the frame of (n ? n : mrd-1), reduced on the device."""
+        torch = self.torch
+        acc = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib().mb_useful_iterations(self.out.data_ptr(), self.out.numel(), self.spec.mrd,
+                                                 acc.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        return int(acc.item())
+
+
+def queue_name() -> str:
+    return f"/mbq_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"

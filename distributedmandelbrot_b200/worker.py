@@ -1,0 +1,201 @@
+"""Drop-in worker: the host side of the hot path, mirroring the reference worker module
+DistributedMandelbrotWorkerCUDA/DistributedMandelbrotWorkerCUDA.py (".py" below).
+
+Same module-level names, same wire protocol, same function boundary:
+
+    process_workload(level, mrd, index_real, index_imag) -> np.ndarray[uint8, 4096*4096]   (.py:70-100)
+    calc_mb_value(r, i, mrd, out=None) -> int32 counts                                     (.py:39-68)
+    receive_workload(sock) -> (level, mrd, indexReal, indexImag)                           (.py:102-109)
+    do_workload_single(addr, port) -> bool                                                 (.py:111-176)
+    main()                                                                                 (.py:178-184)
+
+What changed underneath: coordinates are generated inside the CUDA kernel from an 88-byte tile
+descriptor (the reference builds two 128 MiB float64 arrays on the host and copies them to the
+device, .py:82-88), the escape loop is a hand-written sm_100a kernel with strict (non
+FMA-contracted) binary64 arithmetic, and the uint8 scaling of .py:96-98 is fused into the
+kernel epilogue, so the only device->host traffic is the 16 MiB payload itself.
+
+There is no CPU fallback: every compute function raises if the CUDA library or device is
+missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import socket
+from struct import pack, unpack
+
+import numpy as np
+
+from . import _native as nat
+
+# .py:7-8 / DataChunk.cs:14-15
+MIN_AXIS = -2
+MAX_AXIS = 2
+
+# .py:10-17 / Distributer.cs:30-45
+REQUEST_CODE = 0x00
+RESPONSE_CODE = 0x01
+
+WORKLOAD_AVAILABLE_CODE = 0x10
+WORKLOAD_NOT_AVAILABLE_CODE = 0x11
+
+WORKLOAD_ACCEPT_CODE = 0x20
+WORKLOAD_REJECT_CODE = 0x21
+
+# DataChunk.dataChunkRange / dataChunkSize (DataChunk.cs:20,27); .py:80
+DEFINITION = nat.CHUNK_DEFINITION
+DATA_CHUNK_SIZE = DEFINITION * DEFINITION
+
+
+def process_workload(level: int, mrd: int, index_real: int, index_imag: int, *,
+                     definition: int = DEFINITION, out: np.ndarray | None = None) -> np.ndarray:
+    """(.py:70-100) one DataChunk -> uint8[definition*definition], row-major, p = row*d + col.
+
+    Synchronous; returns a fresh C-contiguous host array owned by the caller (or fills `out`,
+    e.g. a pinned buffer).  Raises ValueError for level == 0 / index >= level (the checks of the
+    DataChunk ctor, DataChunk.cs:99-106) and mrd == 0 (division by zero at .py:96).
+    """
+    nat.ensure_init()
+    n = int(definition) * int(definition)
+    if out is None:
+        out = np.empty(n, dtype=np.uint8)
+    elif out.dtype != np.uint8 or out.size != n or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 array of definition*definition elements")
+    _check_u32(level=level, mrd=mrd, index_real=index_real, index_imag=index_imag, definition=definition)
+    nat.check(nat.lib().mb_process_workload_u8(level, mrd, index_real, index_imag, definition,
+                                               out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def process_workload_counts(level: int, mrd: int, index_real: int, index_imag: int, *,
+                            definition: int = DEFINITION, dtype: str = "f64") -> np.ndarray:
+    """The int32 iteration counts calc_mb_value produces for the chunk, i.e. `out` at .py:94
+    before the uint8 scaling.  dtype "f32" selects the binary32 variant (no upstream counterpart)."""
+    nat.ensure_init()
+    _check_u32(level=level, mrd=mrd, index_real=index_real, index_imag=index_imag, definition=definition)
+    out = np.empty(int(definition) * int(definition), dtype=np.int32)
+    nat.check(nat.lib().mb_process_workload_counts(level, mrd, index_real, index_imag, definition,
+                                                   nat.DTYPES[dtype], out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def calc_mb_value(r, i, mrd: int, out: np.ndarray | None = None) -> np.ndarray:
+    """(.py:39-68) element-wise escape count over explicit coordinate arrays, like the
+    reference's numba ufunc `int32(float64, float64, int32)`.  r and i broadcast together."""
+    nat.ensure_init()
+    r64 = np.asarray(r, dtype=np.float64)
+    i64 = np.asarray(i, dtype=np.float64)
+    r64, i64 = np.broadcast_arrays(r64, i64)
+    shape = r64.shape
+    r64 = np.ascontiguousarray(r64).ravel()
+    i64 = np.ascontiguousarray(i64).ravel()
+    if not (0 <= int(mrd) <= 0x7FFFFFFF):
+        raise ValueError("mrd must fit int32 (.py:39)")
+    if out is None:
+        out = np.empty(shape, dtype=np.int32)
+    elif out.dtype != np.int32 or out.shape != shape or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous int32 array of the broadcast shape")
+    nat.check(nat.lib().mb_calc_mb_value(r64.ctypes.data_as(C.c_void_p), i64.ctypes.data_as(C.c_void_p),
+                                         r64.size, int(mrd), nat.DTYPE_F64, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def _check_u32(**kw) -> None:
+    for name, v in kw.items():
+        if not (0 <= int(v) <= 0xFFFFFFFF):
+            raise ValueError(f"{name}={v} is not a uint32 (DistributerWorkload.cs:61-75)")
+
+
+# ---- wire protocol (.py:102-176 ; Distributer.cs:230-270,358-458 ; DistributerWorkload.cs:53-100)
+
+def _recv_exact(sock: socket.socket, n: int) -> bytes:
+    """The reference calls sock.recv(4) without a length loop (.py:104-107); loop here."""
+    buf = bytearray()
+    while len(buf) < n:
+        part = sock.recv(n - len(buf))
+        if not part:
+            raise ConnectionError(f"connection closed after {len(buf)} of {n} bytes")
+        buf += part
+    return bytes(buf)
+
+
+def receive_workload(sock: socket.socket):
+    """(.py:102-109) four little-endian uint32: level, mrd, indexReal, indexImag
+    (Workload.Send, DistributerWorkload.cs:53-77)."""
+    level, mrd, indexReal, indexImag = unpack("<IIII", _recv_exact(sock, 16))
+    return level, mrd, indexReal, indexImag
+
+
+def request_workload(addr: str, port: int):
+    """First half of do_workload_single (.py:115-134): returns the workload tuple, or None when
+    the Distributer answers WORKLOAD_NOT_AVAILABLE (0x11)."""
+    sock = socket.socket()
+    try:
+        sock.connect((addr, port))
+        sock.sendall(pack("B", REQUEST_CODE))
+        response = _recv_exact(sock, 1)[0]
+        if response == WORKLOAD_AVAILABLE_CODE:
+            return receive_workload(sock)
+        if response == WORKLOAD_NOT_AVAILABLE_CODE:
+            return None
+        raise Exception("Unknown response code to request: " + str(response))
+    finally:
+        sock.close()   # never compute while connected: the server has a 100 ms receive timeout (Distributer.cs:17,196-202)
+
+
+def return_workload(addr: str, port: int, workload, out: np.ndarray) -> bool:
+    """Second half of do_workload_single (.py:148-172): True if the result was accepted and sent,
+    False if the Distributer rejected it (0x21: unknown or timed-out lease) -- not an error."""
+    sock = socket.socket()
+    try:
+        sock.connect((addr, port))
+        sock.sendall(pack("B", RESPONSE_CODE) + pack("<IIII", *workload))
+        response = _recv_exact(sock, 1)[0]
+        if response == WORKLOAD_REJECT_CODE:
+            return False
+        if response != WORKLOAD_ACCEPT_CODE:
+            raise Exception("Unknown response code to request: " + str(response))
+        # exactly dataChunkSize bytes (Distributer.cs:415-416); sendall, the server reads once
+        sock.sendall(memoryview(out).cast("B"))
+        return True
+    finally:
+        sock.close()
+
+
+def do_workload_single(addr: str, port: int, *, verbose: bool = True) -> bool:
+    """(.py:111-176) request one workload, compute it, send it back.  False = no work left."""
+    say = print if verbose else (lambda *a, **k: None)
+    workload = request_workload(addr, port)
+    if workload is None:
+        say("No workload was available, ending program")
+        return False
+    say("Workload received:", workload)
+    say("Starting calculation...")
+    out = process_workload(workload[0], workload[1], workload[2], workload[3])
+    say("Calculation complete")
+    if return_workload(addr, port, workload, out):
+        say("Sent response")
+        say("Process complete")
+    else:
+        say("Response rejected")
+    return True
+
+
+def main(argv=None) -> None:
+    """(.py:178-184) prompts `Server Addr> ` / `Server Port> ` like the reference; --addr/--port/
+    --device skip the prompts."""
+    import argparse
+    ap = argparse.ArgumentParser(description="B200 worker for the DistributedMandelbrot Distributer")
+    ap.add_argument("--addr")
+    ap.add_argument("--port", type=int)
+    ap.add_argument("--device", type=int, default=None)
+    args = ap.parse_args(argv)
+    addr = args.addr if args.addr is not None else input("Server Addr> ")
+    port = args.port if args.port is not None else int(input("Server Port> "))
+    nat.ensure_init(args.device)
+    while do_workload_single(addr, port):
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,214 @@
+/*
+ * mandelbrot_b200.h -- C-ABI of the B200-native escape-time tile renderer.
+ *
+ * This is the drop-in boundary for ONE hot path of ofsouzap/DistributedMandelbrot: the
+ * per-pixel z <- z^2 + c escape-time iteration over a DataChunk tile.  The reference exposes
+ * no FFI of its own; the entry points below are what a binding for this path
+ * would bind, each one citing the reference interface it replaces.  Paths are relative to the
+ * reference root; ".py" = DistributedMandelbrotWorkerCUDA/DistributedMandelbrotWorkerCUDA.py.
+ *
+ * Conventions
+ *   - extern "C", plain C types, no exceptions across the boundary, no torch types.
+ *   - every function returns MB_OK (0) or a negative mb_status; mb_last_error() gives the
+ *     message for the calling thread.
+ *   - the caller owns every buffer; the library never frees caller memory.
+ *   - `*_dev` pointers are device pointers valid on the device passed to mb_init() for the
+ *     calling thread (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as
+ *     void* (NULL = the legacy default stream).  Device-pointer entry points only ENQUEUE
+ *     work on `stream`; host-pointer entry points are synchronous.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with MB_ERR_CUDA.
+ */
+#ifndef MANDELBROT_B200_H
+#define MANDELBROT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+typedef enum mb_status {
+    MB_OK = 0,
+    MB_ERR_INVALID = -1,   /* bad argument (level == 0, index >= level, mrd out of range, ...) */
+    MB_ERR_CUDA = -2,      /* CUDA runtime error / no device */
+    MB_ERR_NOMEM = -3,
+    MB_ERR_STATE = -4,     /* mb_init() not called on this thread's device */
+    MB_ERR_SYS = -5        /* shm / OS error (tile queue) */
+} mb_status;
+
+/* arithmetic type of the iteration */
+#define MB_DTYPE_F64 0     /* the reference's only type: int32(float64, float64, int32), .py:39 */
+#define MB_DTYPE_F32 1     /* binary32 variant (no upstream counterpart) */
+
+/* DataChunk constants (DataChunk.cs:14-15,20,27 ; .py:7-8,80) */
+#define MB_MIN_AXIS (-2.0)
+#define MB_MAX_AXIS (2.0)
+#define MB_CHUNK_DEFINITION 4096u
+
+/*
+ * Tile descriptor: a sub-rectangle of one DataChunk's pixel grid.
+ *
+ * The six doubles are the chunk-level numpy.linspace parameters of .py:24-32 computed on the
+ * host (mb_chunk_geometry) so that host and device share bits:
+ *   v[k] = fl(fl(k*step) + start)  for k < definition-1 ;  v[definition-1] = stop.
+ * Pixel (row, col) of the CHUNK has c = (r[col], i[row])  (.py:34-35: np.tile / np.repeat).
+ * The tile covers chunk columns [x0, x0+w) and rows [y0, y0+h); its pixel (row, col) is
+ * written to out[out_offset + (row-y0)*out_pitch + (col-x0)].  A tile never re-linspaces
+ * itself: it indexes into the chunk-level grid.
+ */
+typedef struct mb_tile {
+    double start_r, start_i;
+    double stop_r, stop_i;
+    double step_r, step_i;
+    uint32_t definition;   /* samples per axis of the chunk (reference: 4096) */
+    uint32_t mrd;          /* maximum recursion depth: updates n = 1 .. mrd-1 (.py:47) */
+    uint32_t x0, y0, w, h;
+    uint64_t out_offset;   /* in elements */
+    uint32_t out_pitch;    /* elements between successive tile rows in out */
+    uint32_t flags;        /* reserved, must be 0 */
+} mb_tile;                 /* 88 bytes */
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+
+/* Bind the calling thread to CUDA device `device` and create the library context for it. */
+int mb_init(int device);
+void mb_shutdown(void);
+const char *mb_last_error(void);
+int mb_abi_version(void);
+/* number of CUDA devices, or a negative mb_status */
+int mb_device_count(void);
+/* SM count of the bound device (148 on B200) */
+int mb_sm_count(void);
+
+/* ---- geometry (host only, no GPU needed) --------------------------------------------- */
+
+/*
+ * Replaces .py:75-78 (chunk_range / start_r / start_i) == DataChunk.GetLevelChunkRange
+ * (DataChunk.cs:32-33) + StartValueReal/Imag (DataChunk.cs:59-66), and the linspace
+ * parameters of gen_arrays (.py:24-32).  Every operation individually rounded in binary64.
+ * Fills a whole-chunk tile (x0 = y0 = 0, w = h = definition, out_offset = 0,
+ * out_pitch = definition).  Errors like the DataChunk ctor (DataChunk.cs:99-106):
+ * level == 0, index >= level -> MB_ERR_INVALID.  definition must be >= 1, mrd <= INT32_MAX
+ * (the reference kernel takes int32 mrd, .py:39).
+ */
+int mb_chunk_geometry(uint32_t level, uint32_t index_real, uint32_t index_imag,
+                      uint32_t definition, uint32_t mrd, mb_tile *out);
+
+/* one linspace sample of a tile axis, exactly as the device computes it (for tests) */
+double mb_tile_coord(const mb_tile *t, int axis /*0 = real, 1 = imag*/, uint32_t k);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+
+/*
+ * Replaces calc_mb_value (.py:39-68) together with gen_arrays (.py:19-37): int32 escape
+ * counts for `n_tiles` tiles, written to out_dev.  One CUDA thread per pixel; coordinates are
+ * generated in-kernel from the descriptors (nothing but 88 bytes per tile is read).
+ * Count semantics (.py:44-68): z0 = c; n = 1..mrd-1: z <- z^2 + c; first n with |z|^2 >= 4,
+ * else 0.
+ */
+int mb_render_counts(const mb_tile *tiles, uint32_t n_tiles, int32_t *out_dev, int dtype,
+                     void *stream);
+
+/*
+ * calc_mb_value exactly as the reference calls it at .py:92: explicit float64 coordinate
+ * arrays (device pointers, n elements each) -> int32 counts.  One thread per element.
+ */
+int mb_calc_mb_value_dev(const double *r_dev, const double *i_dev, size_t n, uint32_t mrd,
+                         int dtype, int32_t *out_dev, void *stream);
+/* host-pointer convenience form of the same (copies in, runs, copies out; synchronous) */
+int mb_calc_mb_value(const double *r_host, const double *i_host, size_t n, uint32_t mrd,
+                     int dtype, int32_t *out_host);
+
+/*
+ * Same, with the uint8 scaling of .py:96-98 fused into the kernel epilogue:
+ * u = uint8(ceil(float64(n) * 256 / mrd)), including the 256 -> 0 wrap.
+ * This is the DataChunk payload (DataChunk.cs:20,27,77): one byte per pixel.
+ */
+int mb_render_u8(const mb_tile *tiles, uint32_t n_tiles, uint8_t *out_dev, int dtype,
+                 void *stream);
+
+/* Stand-alone uint8 epilogue (.py:96-98) over n device int32 counts. */
+int mb_counts_to_u8(const int32_t *counts_dev, uint8_t *out_dev, size_t n, uint32_t mrd,
+                    void *stream);
+
+/*
+ * Metric helper: sum over pixels of (n ? n : mrd-1) = pixel-iterations the reference
+ * semantics require.  Accumulates INTO *sum_dev (a device uint64 the caller
+ * zeroes); asynchronous on `stream`.
+ */
+int mb_useful_iterations(const int32_t *counts_dev, size_t n, uint32_t mrd, uint64_t *sum_dev,
+                         void *stream);
+
+/*
+ * Chunk classification used by the server on arrival (DataChunk.IsNeverChunk /
+ * IsImmediateChunk, DataChunk.cs:82,87): flags_dev[0] = 1 iff every byte == 0,
+ * flags_dev[1] = 1 iff every byte == 1.  Asynchronous on `stream`.
+ */
+int mb_classify_u8(const uint8_t *payload_dev, size_t n, uint32_t *flags_dev, void *stream);
+
+/* ---- one-call equivalents of process_workload (host buffers, synchronous) ------------- */
+
+/*
+ * Replaces process_workload(level, mrd, index_real, index_imag) -> uint8[definition^2]
+ * (.py:70-100); the reference fixes definition = 4096 (.py:80).  host_out may be pageable or
+ * pinned memory of definition^2 bytes.  The device->host copy is inside the call.
+ */
+int mb_process_workload_u8(uint32_t level, uint32_t mrd, uint32_t index_real,
+                           uint32_t index_imag, uint32_t definition, uint8_t *host_out);
+
+/* same, int32 counts (what calc_mb_value returns before .py:96), definition^2 * 4 bytes */
+int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real,
+                               uint32_t index_imag, uint32_t definition, int dtype,
+                               int32_t *host_out);
+
+/* ---- in-box tile dispatch: lock-free work-stealing ranges in POSIX shared memory ------- */
+/*
+ * Replaces Distributer.TryGetNextNeededWorkload / HandleWorkloadRequest
+ * (Distributer.cs:335-392) for the in-box path: instead of leasing chunks over TCP, the
+ * `n_ranks` GPU processes of one box share a shm segment holding one [head, tail) range of
+ * tile indices per rank (a static contiguous split of [0, total)).  A rank pops from the head
+ * of its own range; when that is empty it steals the upper half of the fullest victim's range.
+ * All operations are single 64-bit CAS; every index in [0, total) is handed out exactly once.
+ * Host-only: usable without a GPU.
+ */
+typedef struct mb_wsq mb_wsq;
+
+/* rank 0: create + initialise (name like "/mbq_1234"); others: open after a barrier */
+int mb_wsq_create(const char *name, uint32_t n_ranks, uint32_t total, mb_wsq **out);
+int mb_wsq_open(const char *name, mb_wsq **out);
+/* re-arm the same segment for another pass over [0, total) (call on one rank, between barriers) */
+int mb_wsq_reset(mb_wsq *q, uint32_t total);
+/*
+ * Claim up to `want` consecutive indices for `rank`.  Returns 1 and sets [*first, *first + *got)
+ * when work was obtained (*stolen = 1 if it came from another rank's range), 0 when the whole
+ * queue is drained, negative mb_status on error.
+ */
+int mb_wsq_pop(mb_wsq *q, uint32_t rank, uint32_t want, uint32_t *first, uint32_t *got,
+               uint32_t *stolen);
+int mb_wsq_close(mb_wsq *q);
+int mb_wsq_unlink(const char *name);
+
+/* ---- roofline denominators, measured on the bound device ------------------------------ */
+/*
+ * Dependency-free DFMA (dtype F64) / FFMA (F32) issue-rate microbenchmark: every SM runs
+ * `chains` independent FMA chains per thread for `iters` steps.  *tera_fma_per_s = FMA-pipe
+ * warp-lane operations per second / 1e12 (multiply by 2 for FLOP/s).  Synchronous.
+ */
+int mb_measure_fma_peak(int dtype, int iters, double *tera_fma_per_s, float *elapsed_ms);
+/*
+ * Same harness, selectable instruction mix: mode 0 = independent FMA chains (as above),
+ * mode 1 = the 7-instruction Mandelbrot update (3 MUL, 3 ADD/SUB, 1 FMA) with no escape test
+ * and no divergence -- the arithmetic ceiling of the escape loop itself.
+ * *tera_ops_per_s counts FMA-pipe lane operations per second / 1e12.
+ */
+int mb_measure_pipe_rate(int dtype, int mode, int iters, double *tera_ops_per_s,
+                         float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANDELBROT_B200_H */

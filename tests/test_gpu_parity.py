@@ -1,0 +1,241 @@
+"""Parity tests proper: the sm_100a kernels, called through the C-ABI, against the golden
+vectors (reference function text) and the CPU oracle.  Bit-exact: integer/index results."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _render(native, tiles, n_out, dtype="f64", u8=False):
+    import torch
+    arr = native.tile_array(tiles)
+    out = torch.full((n_out,), 77 if u8 else -7, dtype=torch.uint8 if u8 else torch.int32, device="cuda")
+    fn = native.lib().mb_render_u8 if u8 else native.lib().mb_render_counts
+    native.check(fn(arr, len(tiles), out.data_ptr(), native.DTYPES[dtype], torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_golden_small_counts_and_u8(gpu, golden_meta, golden_arrays):
+    from distributedmandelbrot_b200 import worker
+    for rec in golden_meta["small"]:
+        d = rec["d"]
+        args = (rec["level"], rec["mrd"], rec["ir"], rec["ii"])
+        counts = worker.process_workload_counts(*args, definition=d)
+        assert np.array_equal(counts.reshape(d, d), golden_arrays[rec["key"] + "_counts"]), rec
+        u8 = worker.process_workload(*args, definition=d)
+        assert u8.dtype == np.uint8 and u8.shape == (d * d,) and u8.flags.c_contiguous
+        assert np.array_equal(u8.reshape(d, d), golden_arrays[rec["key"] + "_u8"]), rec
+
+
+def test_golden_medium_hashes(gpu, oracle, golden_meta):
+    from distributedmandelbrot_b200 import worker
+    for rec in golden_meta["medium"]:
+        d = rec["d"]
+        args = (rec["level"], rec["mrd"], rec["ir"], rec["ii"])
+        counts = worker.process_workload_counts(*args, definition=d)
+        assert oracle.useful_iterations(counts, rec["mrd"]) == rec["useful"], rec
+        assert f"{oracle.fnv1a_words(counts):016x}" == rec["fnv"], rec
+        u8 = worker.process_workload(*args, definition=d)
+        assert hashlib.sha256(u8.tobytes()).hexdigest() == rec["u8_sha256"], rec
+
+
+def test_process_workload_native_chunk_is_reference_shape(gpu, golden_meta):
+    """process_workload(level, mrd, ir, ii) with the reference's fixed 4096 definition (.py:80)."""
+    from distributedmandelbrot_b200 import worker
+    rec = [r for r in golden_meta["medium"] if r["d"] == 4096][0]
+    out = worker.process_workload(rec["level"], rec["mrd"], rec["ir"], rec["ii"])
+    assert out.shape == (4096 * 4096,) and out.dtype == np.uint8
+    assert hashlib.sha256(out.tobytes()).hexdigest() == rec["u8_sha256"]
+
+
+@pytest.mark.parametrize("case", [
+    # level, ir, ii, d, mrd
+    (1, 0, 0, 200, 500), (2, 1, 0, 129, 1000), (6, 2, 3, 256, 2000), (16, 4, 8, 256, 1024),
+    (10, 3, 5, 300, 1024), (800, 250, 420, 160, 10000), (4000000, 1256353, 2131821, 96, 20000),
+    (7, 6, 0, 2, 5), (5, 2, 2, 1, 100), (3, 0, 2, 31, 1), (3, 0, 2, 33, 2), (12, 5, 6, 100, 9),
+])
+def test_counts_vs_oracle(gpu, oracle, case):
+    from distributedmandelbrot_b200 import worker
+    level, ir, ii, d, mrd = case
+    got = worker.process_workload_counts(level, mrd, ir, ii, definition=d).reshape(d, d)
+    want = oracle.render_chunk_counts(level, mrd, ir, ii, d)
+    assert np.array_equal(got, want), case
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_sub_rectangles_and_strides(gpu, oracle, seed):
+    """Ragged tiles: odd origins/sizes, padded pitch, unaligned offsets (scalar-store fallback),
+    several tiles of different shape in one launch, int32 and fused-uint8 outputs."""
+    rng = np.random.default_rng(100 + seed)
+    level = int(rng.integers(1, 30))
+    ir, ii = int(rng.integers(0, level)), int(rng.integers(0, level))
+    d = int(rng.integers(40, 200))
+    mrd = int(rng.choice([2, 64, 300, 1500]))
+    chunk = gpu.chunk_geometry(level, ir, ii, d, mrd)
+    whole = oracle.render_chunk_counts(level, mrd, ir, ii, d)
+    tiles, places, off = [], [], int(rng.integers(0, 5))
+    for _ in range(int(rng.integers(1, 7))):
+        w, h = int(rng.integers(1, d + 1)), int(rng.integers(1, d + 1))
+        x0, y0 = int(rng.integers(0, d - w + 1)), int(rng.integers(0, d - h + 1))
+        pitch = w + int(rng.integers(0, 6))
+        tiles.append(chunk.sub(x0, y0, w, h, off, pitch))
+        places.append((x0, y0, w, h, off, pitch))
+        off += pitch * h + int(rng.integers(0, 9))
+    for u8 in (False, True):
+        if u8 and mrd == 0:
+            continue
+        out = _render(gpu, tiles, off + 8, u8=u8)
+        fill = 77 if u8 else -7
+        touched = np.zeros(off + 8, bool)
+        for (x0, y0, w, h, o, pitch) in places:
+            want = whole[y0:y0 + h, x0:x0 + w]
+            if u8:
+                want = oracle.counts_to_u8(want, mrd)
+            idx = (o + np.arange(h)[:, None] * pitch + np.arange(w)[None, :])
+            assert np.array_equal(out[idx], want), (seed, u8, x0, y0, w, h, o, pitch)
+            touched[idx] = True
+        assert (out[~touched] == fill).all(), "kernel wrote outside its tiles"
+
+
+def test_bands_equal_whole_chunk(gpu, oracle):
+    """Tiling invariance: a chunk rendered as row bands / column strips == rendered whole."""
+    level, ir, ii, d, mrd = 10, 3, 5, 512, 1024
+    chunk = gpu.chunk_geometry(level, ir, ii, d, mrd)
+    whole = _render(gpu, [chunk], d * d).reshape(d, d)
+    bands = [chunk.sub(0, y, d, 64, y * d, d) for y in range(0, d, 64)]
+    assert np.array_equal(_render(gpu, bands, d * d).reshape(d, d), whole)
+    strips = [chunk.sub(x, 0, 100 if x + 100 <= d else d - x, d, x, d) for x in range(0, d, 100)]
+    assert np.array_equal(_render(gpu, strips, d * d).reshape(d, d), whole)
+    assert np.array_equal(whole, oracle.render_chunk_counts(level, mrd, ir, ii, d))
+
+
+def test_f32_variant_vs_oracle(gpu, oracle, golden_meta, golden_arrays):
+    from distributedmandelbrot_b200 import worker
+    for rec in golden_meta["f32"]:
+        d = rec["d"]
+        got = worker.process_workload_counts(rec["level"], rec["mrd"], rec["ir"], rec["ii"], definition=d, dtype="f32")
+        assert np.array_equal(got.reshape(d, d), golden_arrays[rec["key"] + "_counts"]), rec
+    for (level, ir, ii, d, mrd) in [(4, 1, 1, 256, 4096), (4, 2, 1, 300, 700), (1, 0, 0, 257, 333)]:
+        got = worker.process_workload_counts(level, mrd, ir, ii, definition=d, dtype="f32").reshape(d, d)
+        assert np.array_equal(got, oracle.render_chunk_counts(level, mrd, ir, ii, d, dtype="f32"))
+
+
+def test_calc_mb_value_points(gpu, oracle):
+    """The reference's ufunc boundary (.py:39-42,92): arbitrary coordinates, incl. |c| >= 2, the
+    real axis, -2, the cusp 0.25, -0.75, and a cloud of points around the boundary."""
+    from distributedmandelbrot_b200 import worker
+    rng = np.random.default_rng(5)
+    th = rng.uniform(0, 2 * np.pi, 3000)
+    card_r = 0.5 * np.cos(th) - 0.25 * np.cos(2 * th)
+    card_i = 0.5 * np.sin(th) - 0.25 * np.sin(2 * th)
+    jit = rng.normal(0, 1e-3, (2, 3000))
+    r = np.concatenate([[2.0, -2.0, 0.0, 0.25, -0.75, -0.75, 3.0, -2.0000000000000004, 1e-300, 0.0],
+                        card_r + jit[0], rng.uniform(-2, 2, 2000)])
+    i = np.concatenate([[2.0, 0.0, 0.0, 0.0, 0.0, 1e-9, 0.0, 0.0, 1e-300, 5e-324],
+                        card_i + jit[1], rng.uniform(-2, 2, 2000)])
+    for mrd in (1, 2, 50, 3000):
+        got = worker.calc_mb_value(r, i, mrd)
+        want = np.array([oracle.escape_f64(a, b, mrd) for a, b in zip(r, i)], np.int32)
+        assert np.array_equal(got, want), mrd
+    # broadcasting like a ufunc
+    g = worker.calc_mb_value(np.linspace(-2, 1, 7)[None, :], np.linspace(-1, 1, 5)[:, None], 30)
+    assert g.shape == (5, 7)
+
+
+def test_u8_epilogue_standalone_and_fused(gpu, golden_meta, golden_arrays):
+    import torch
+    for rec in golden_meta["u8"]:
+        mrd = rec["mrd"]
+        counts = torch.arange(mrd, dtype=torch.int32, device="cuda")
+        out = torch.empty(mrd, dtype=torch.uint8, device="cuda")
+        gpu.check(gpu.lib().mb_counts_to_u8(counts.data_ptr(), out.data_ptr(), mrd, mrd, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), golden_arrays[rec["key"]]), mrd
+    # unaligned pointers take the scalar path
+    counts = torch.arange(1001, dtype=torch.int32, device="cuda")[1:]
+    out = torch.empty(1001, dtype=torch.uint8, device="cuda")[1:]
+    gpu.check(gpu.lib().mb_counts_to_u8(counts.data_ptr(), out.data_ptr(), 1000, 1001, None))
+    torch.cuda.synchronize()
+    n = np.arange(1, 1001, dtype=np.int64)
+    assert np.array_equal(out.cpu().numpy(), (((n * 256 + 1000) // 1001) & 0xFF).astype(np.uint8))
+
+
+def test_useful_iterations_and_classify(gpu, oracle):
+    import torch
+    from distributedmandelbrot_b200 import worker
+    counts = worker.process_workload_counts(10, 1024, 3, 5, definition=384)
+    dev = torch.from_numpy(counts).cuda()
+    acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    gpu.check(gpu.lib().mb_useful_iterations(dev.data_ptr(), dev.numel(), 1024, acc.data_ptr(), None))
+    assert int(acc.item()) == oracle.useful_iterations(counts, 1024)
+    flags = torch.empty(2, dtype=torch.int32, device="cuda")
+    for payload, want in [(np.zeros(5000, np.uint8), [1, 0]), (np.ones(5000, np.uint8), [0, 1]),
+                          (np.r_[np.zeros(4999, np.uint8), np.uint8(1)], [0, 0])]:
+        p = torch.from_numpy(payload).cuda()
+        gpu.check(gpu.lib().mb_classify_u8(p.data_ptr(), p.numel(), flags.data_ptr(), None))
+        assert flags.cpu().tolist() == want
+    # the reference's own classification cases: an all-never and an all-immediate chunk
+    never = worker.process_workload(16, 300, 5, 8, definition=128)        # inside the main cardioid
+    assert not never.any()
+    immediate = worker.process_workload(4, 100, 0, 0, definition=64)      # far corner: escapes at n <= 2
+    assert immediate.min() >= 1
+
+
+def test_invalid_arguments_raise(gpu):
+    from distributedmandelbrot_b200 import worker
+    for args in [(0, 10, 0, 0), (4, 10, 4, 0), (4, 10, 0, 4), (4, 0, 1, 1)]:
+        with pytest.raises(ValueError):
+            worker.process_workload(*args, definition=16)
+    with pytest.raises(ValueError):
+        worker.process_workload(4, 2**31, 1, 1, definition=16)
+    with pytest.raises(ValueError):
+        worker.process_workload(4, 10, 1, 1, definition=16, out=np.empty(5, np.uint8))
+
+
+# ---- BASELINE sizes: size-independent properties ------------------------------------------------
+
+def test_cfg2_full_frame_vs_oracle(gpu, oracle):
+    """cfg2 (4096^2 whole plane, mrd 1024, 256 chunks of 256^2) is small enough for a full compare."""
+    from distributedmandelbrot_b200.frame import CONFIGS, FrameRenderer
+    spec = CONFIGS["cfg2"]
+    fr = FrameRenderer(spec, device=0)
+    fr.render_all()
+    got = fr.out.cpu().numpy().reshape(spec.n_chunks, spec.definition, spec.definition)
+    total = 0
+    for c, (ir, ii) in enumerate(spec.chunk_indices()):
+        want = oracle.render_chunk_counts(spec.level, spec.mrd, ir, ii, spec.definition)
+        assert np.array_equal(got[c], want), (ir, ii)
+        total += oracle.useful_iterations(want, spec.mrd)
+    assert fr.useful_iterations() == total
+
+
+def test_full_size_chunk_properties(gpu, oracle):
+    """A native 4096^2 chunk of the cfg4 frame at mrd = 10000: determinism, tiling invariance,
+    mrd-monotonicity (a pixel that escaped at n under mrd1 escapes at the same n under any larger
+    mrd; one that did not must give 0 or >= mrd1), fused uint8 == epilogue(int32), plus an exact
+    comparison of a strided sample of rows against the oracle."""
+    import torch
+    from distributedmandelbrot_b200.frame import CONFIGS
+    spec = CONFIGS["cfg4"]
+    d = spec.definition
+    ir, ii = 250, 420                       # the chunk whose corner is the zoom centre -0.75+0.1i
+    hi = gpu.chunk_geometry(spec.level, ir, ii, d, 10000)
+    lo = gpu.chunk_geometry(spec.level, ir, ii, d, 700)
+    a = _render(gpu, [hi], d * d)
+    assert np.array_equal(a, _render(gpu, [hi], d * d))                                # idempotent
+    bands = [hi.sub(0, y, d, 512, y * d, d) for y in range(0, d, 512)]
+    assert np.array_equal(a, _render(gpu, bands, d * d))                               # tiling invariance
+    b = _render(gpu, [lo], d * d)
+    esc = b != 0
+    assert np.array_equal(a[esc], b[esc])
+    assert ((a[~esc] == 0) | (a[~esc] >= 700)).all()
+    u8 = _render(gpu, [hi], d * d, u8=True)
+    assert np.array_equal(u8, oracle.counts_to_u8(a, 10000))
+    rows = list(range(0, d, 293))
+    for y in rows:
+        want = oracle.render_chunk_counts(spec.level, 10000, ir, ii, d, x0=0, y0=y, w=d, h=1)
+        assert np.array_equal(a.reshape(d, d)[y], want[0]), y

@@ -1,0 +1,109 @@
+"""Host side of the C-ABI without a GPU: the library loads, exports every symbol the header
+declares, computes chunk geometry exactly, and fails loudly (no CPU fallback) on compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "mandelbrot_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(native):
+    lib = C.CDLL(native.library_path())
+    declared = _declared_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mandelbrot_b200.h but not exported"
+    # and the Python binding declares a signature for each of them
+    assert set(declared) == set(native.SIGNATURES), set(declared) ^ set(native.SIGNATURES)
+
+
+def test_tile_struct_layout(native):
+    assert C.sizeof(native.Tile) == 88
+    assert native.Tile.definition.offset == 48 and native.Tile.out_offset.offset == 72
+
+
+def test_chunk_geometry_matches_reference_formulas(native, golden_meta, golden_arrays):
+    for rec in golden_meta["linspace"]:
+        level, ir, ii, d = rec["level"], rec["ir"], rec["ii"], rec["d"]
+        t = native.chunk_geometry(level, ir, ii, d, 100)
+        chunk_range = (2 - (-2)) / level                  # .py:75
+        assert t.start_r == -2 + (chunk_range * ir)       # .py:77
+        assert t.start_i == -2 + (chunk_range * ii)       # .py:78
+        assert t.stop_r == t.start_r + chunk_range and t.stop_i == t.start_i + chunk_range
+        r = np.array([native.lib().mb_tile_coord(C.byref(t), 0, k) for k in range(d)])
+        i = np.array([native.lib().mb_tile_coord(C.byref(t), 1, k) for k in range(d)])
+        assert np.array_equal(r, golden_arrays[rec["key"] + "_r"])      # gen_arrays output (.py:19-37)
+        assert np.array_equal(i, golden_arrays[rec["key"] + "_i"])
+        assert np.array_equal(r, np.linspace(t.start_r, t.start_r + chunk_range, d))
+        assert (t.x0, t.y0, t.w, t.h, t.out_offset, t.out_pitch, t.mrd) == (0, 0, d, d, 0, d, 100)
+
+
+def test_chunk_geometry_random_levels(native):
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        level = int(rng.integers(1, 5_000_000))
+        ir, ii = int(rng.integers(0, level)), int(rng.integers(0, level))
+        d = int(rng.choice([2, 3, 255, 256, 4096]))
+        t = native.chunk_geometry(level, ir, ii, d, 1)
+        chunk_range = 4 / level
+        start = -2 + chunk_range * ir
+        ref = np.linspace(start, start + chunk_range, d)
+        ks = [0, 1, d // 2, d - 2, d - 1]
+        got = [native.lib().mb_tile_coord(C.byref(t), 0, k) for k in ks]
+        assert got == [ref[k] for k in ks]
+
+
+def test_definition_one_is_linspace_num_1(native):
+    t = native.chunk_geometry(4, 1, 2, 1, 10)
+    assert native.lib().mb_tile_coord(C.byref(t), 0, 0) == np.linspace(-1.0, 0.0, 1)[0]
+
+
+def test_argument_errors_mirror_datachunk_ctor(native):
+    # DataChunk.cs:99-106
+    for args in [(0, 0, 0), (4, 4, 0), (4, 0, 4), (4, 7, 9)]:
+        with pytest.raises(ValueError):
+            native.chunk_geometry(*args, 4096, 10)
+    with pytest.raises(ValueError):
+        native.chunk_geometry(4, 0, 0, 0, 10)             # definition 0
+    with pytest.raises(ValueError):
+        native.chunk_geometry(4, 0, 0, 16, 2**31)         # mrd does not fit the kernel's int32 (.py:39)
+    with pytest.raises(ValueError):
+        native.chunk_geometry(-1, 0, 0, 16, 10)
+
+
+def test_no_cpu_fallback_without_a_device(native):
+    """Where there is no CUDA device, compute entry points must fail, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from distributedmandelbrot_b200 import worker
+    with pytest.raises(native.NativeError):
+        native.init(0)
+    with pytest.raises(native.NativeError):
+        worker.process_workload(4, 256, 1, 2)
+    with pytest.raises(native.NativeError):
+        worker.calc_mb_value(np.zeros(4), np.zeros(4), 10)
+    out = np.zeros(16, np.uint8)
+    rc = native.lib().mb_process_workload_u8(4, 16, 0, 0, 4, out.ctypes.data_as(C.c_void_p))
+    assert rc in (native.MB_ERR_STATE, native.MB_ERR_CUDA)
+    assert not out.any()
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "distributedmandelbrot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "mandel_oracle" not in txt, f
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f

@@ -1,0 +1,112 @@
+"""The CPU oracle against the golden vectors produced by executing the reference's own function
+text (oracle/gen_golden.py), and against an independent numpy restatement."""
+import hashlib
+
+import numpy as np
+import pytest
+
+
+def test_small_cases_bit_exact(oracle, golden_meta, golden_arrays):
+    for rec in golden_meta["small"]:
+        u8, counts = oracle.process_workload(rec["level"], rec["mrd"], rec["ir"], rec["ii"], rec["d"], want_counts=True)
+        d = rec["d"]
+        assert np.array_equal(counts.reshape(d, d), golden_arrays[rec["key"] + "_counts"]), rec
+        assert np.array_equal(u8.reshape(d, d), golden_arrays[rec["key"] + "_u8"]), rec
+        assert oracle.useful_iterations(counts, rec["mrd"]) == rec["useful"]
+
+
+def test_medium_cases_hashes(oracle, golden_meta):
+    for rec in golden_meta["medium"]:
+        if rec["d"] > 1024:
+            continue   # the 4096^2 native chunk is checked in test_native_chunk_golden below
+        u8, counts = oracle.process_workload(rec["level"], rec["mrd"], rec["ir"], rec["ii"], rec["d"], want_counts=True)
+        assert oracle.useful_iterations(counts, rec["mrd"]) == rec["useful"], rec
+        assert f"{oracle.fnv1a_words(counts):016x}" == rec["fnv"], rec
+        assert int((counts == 0).sum()) == rec["zeros"]
+        assert hashlib.sha256(u8.tobytes()).hexdigest() == rec["u8_sha256"], rec
+
+
+def test_native_chunk_golden(oracle, golden_meta):
+    rec = [r for r in golden_meta["medium"] if r["d"] == 4096][0]
+    u8, counts = oracle.process_workload(rec["level"], rec["mrd"], rec["ir"], rec["ii"], 4096, want_counts=True)
+    assert oracle.useful_iterations(counts, rec["mrd"]) == rec["useful"]
+    assert f"{oracle.fnv1a_words(counts):016x}" == rec["fnv"]
+    assert hashlib.sha256(u8.tobytes()).hexdigest() == rec["u8_sha256"]
+
+
+def test_survey_appendix_c_known_answers(oracle):
+    """SURVEY.md Appendix C (survey-time strict oracle): sum of pixel-iterations and zero counts."""
+    for (level, ir, ii, d, mrd, useful, zeros) in [
+        (4, 1, 2, 512, 256, 34_620_920, 129_904),
+        (10, 3, 5, 512, 1024, 219_799_424, 212_832),
+        (20, 6, 10, 256, 1024, 56_839_714, 54_879),
+        (3, 1, 1, 257, 300, 13_531_838, 44_189),
+    ]:
+        c = oracle.render_chunk_counts(level, mrd, ir, ii, d)
+        assert oracle.useful_iterations(c, mrd) == useful
+        assert int((c == 0).sum()) == zeros
+    # window start (-0.8, 0.05), range 0.1
+    c = oracle.render_rect(-0.8, 0.05, 0.1, 512, 1024)
+    assert oracle.useful_iterations(c, 1024) == 197_695_090
+
+
+def test_linspace_matches_numpy_and_golden(oracle, golden_meta, golden_arrays):
+    for rec in golden_meta["linspace"]:
+        rng, sr, si = oracle.chunk_geometry(rec["level"], rec["ir"], rec["ii"])
+        r = oracle.linspace(sr, sr + rng, rec["d"])
+        i = oracle.linspace(si, si + rng, rec["d"])
+        assert np.array_equal(r, golden_arrays[rec["key"] + "_r"])
+        assert np.array_equal(i, golden_arrays[rec["key"] + "_i"])
+        assert np.array_equal(r, np.linspace(sr, sr + rng, rec["d"]))
+        # Python evaluation of .py:75-78
+        chunk_range = (2 - (-2)) / rec["level"]
+        assert rng == chunk_range and sr == -2 + chunk_range * rec["ir"] and si == -2 + chunk_range * rec["ii"]
+
+
+def test_u8_epilogue_all_counts(oracle, golden_meta, golden_arrays):
+    for rec in golden_meta["u8"]:
+        mrd = rec["mrd"]
+        n = np.arange(mrd, dtype=np.int32)
+        got = oracle.counts_to_u8(n, mrd)
+        assert np.array_equal(got, golden_arrays[rec["key"]]), mrd
+        # integer identity used on the device, including the 256 -> 0 wrap
+        ident = (((n.astype(np.int64) * 256 + mrd - 1) // mrd) & 0xFF).astype(np.uint8)
+        assert np.array_equal(got, ident), mrd
+    assert oracle.counts_to_u8(np.array([0, 1021, 1022, 1023], np.int32), 1024).tolist() == [0, 0, 0, 0]
+
+
+def test_f32_oracle_matches_numpy_restatement(oracle, golden_meta, golden_arrays):
+    for rec in golden_meta["f32"]:
+        c = oracle.render_chunk_counts(rec["level"], rec["mrd"], rec["ir"], rec["ii"], rec["d"], dtype="f32")
+        assert np.array_equal(c, golden_arrays[rec["key"] + "_counts"]), rec
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_c_oracle_matches_numpy_restatement_random(oracle, seed):
+    rng = np.random.default_rng(seed)
+    level = int(rng.integers(1, 40))
+    ir, ii = int(rng.integers(0, level)), int(rng.integers(0, level))
+    d = int(rng.integers(2, 70))
+    mrd = int(rng.choice([1, 2, 3, 17, 100, 400]))
+    a = oracle.render_chunk_counts(level, mrd, ir, ii, d)
+    b = oracle.np_process_counts(level, mrd, ir, ii, d)
+    assert np.array_equal(a, b), (level, ir, ii, d, mrd)
+    assert np.array_equal(oracle.counts_to_u8(a, max(mrd, 1)), oracle.np_counts_to_u8(a, max(mrd, 1)))
+
+
+def test_sub_rectangle_indexes_chunk_grid(oracle):
+    """A tile of a chunk indexes the chunk-level linspace, never its own."""
+    whole = oracle.render_chunk_counts(10, 300, 3, 5, 96)
+    part = oracle.render_chunk_counts(10, 300, 3, 5, 96, x0=13, y0=40, w=50, h=33)
+    assert np.array_equal(part, whole[40:73, 13:63])
+
+
+def test_edge_semantics(oracle):
+    # z0 = c is never tested: |c| >= 2 still returns >= 1
+    assert oracle.escape_f64(2.0, 2.0, 10) == 1
+    # c = -2: z1 = 2, |z1|^2 = 4 and the test is `>= 4` (.py:65) -> "escapes" at n = 1
+    assert oracle.escape_f64(-2.0, 0.0, 50) == 1
+    assert oracle.escape_f64(0.0, 0.0, 50) == 0         # never escapes -> 0 (.py:68)
+    assert oracle.escape_f64(3.0, 0.0, 1) == 0          # mrd = 1: range(1, 1) is empty
+    assert oracle.escape_f64(3.0, 0.0, 2) == 1
+    assert oracle.useful_iterations(np.array([0, 1, 5, 0], np.int32), 10) == 9 + 1 + 5 + 9
