@@ -69,6 +69,15 @@ def main():
         r["wall_s"] = time.time() - t0
         res["frames"].append(r)
         print(json.dumps(r), flush=True)
+    if os.environ.get("PROBE_PERCHUNK"):
+        base = CONFIGS[os.environ["PROBE_PERCHUNK"]]
+        rows = []
+        for (ir, ii) in base.chunk_indices():
+            r = time_frame(base.scaled(name=f"{ir},{ii}", blocks=1, ir0=ir, ii0=ii), reps=1)
+            rows.append({"ir": ir, "ii": ii, "useful": r["useful"], "ms": r["ms"][0]})
+        res["perchunk"] = rows
+        tot_u = sum(r["useful"] for r in rows); tot_ms = sum(r["ms"] for r in rows)
+        print("perchunk total useful", tot_u, "ms", tot_ms, "Gpx-it/s", tot_u / tot_ms / 1e6, flush=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w") as f:
         json.dump(res, f, indent=1)
 

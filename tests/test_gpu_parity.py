@@ -179,7 +179,7 @@ def test_useful_iterations_and_classify(gpu, oracle):
         gpu.check(gpu.lib().mb_classify_u8(p.data_ptr(), p.numel(), flags.data_ptr(), None))
         assert flags.cpu().tolist() == want
     # the reference's own classification cases: an all-never and an all-immediate chunk
-    never = worker.process_workload(16, 300, 5, 8, definition=128)        # inside the main cardioid
+    never = worker.process_workload(8, 300, 3, 4, definition=128)         # inside the main cardioid
     assert not never.any()
     immediate = worker.process_workload(4, 100, 0, 0, definition=64)      # far corner: escapes at n <= 2
     assert immediate.min() >= 1
