@@ -57,49 +57,127 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ float coord(double v) { return __double2float_rn(v); }
 };
 
-// One pixel per lane.  `left` (= mrd-1 updates allowed) is uniform over a tile, so the
-// block structure below is warp-uniform: U updates with only the escape test between them,
-// then one warp vote; the whole warp leaves as soon as every lane has escaped or hit mrd.
-template <typename Real, int U>
+// ---- deferred escape test ---------------------------------------------------------------------
+// On B200 a warp-wide FP64 instruction holds an SM sub-partition's issue port for 2 cycles and
+// every other instruction for 1 (measured: profiles/), so the loop is ISSUE bound: testing
+// |z|^2 >= 4 after every update costs 7 FP64 + 3 other instructions = 17 cycles per
+// pixel-iteration (82 % of the DFMA peak, which is what the checked loop reaches).  The steady
+// state below therefore runs K updates with NO test -- and without the magnitude add, which only
+// the test consumes: 6 FP64 instructions per update -- then tests once.  If the orbit escaped
+// somewhere inside the block, the block is REPLAYED from its saved start with a test after every
+// update, so the reported n is the exact first n with fl(fl(x^2)+fl(y^2)) >= 4, as .py:62-66.
+//
+// Why a single test at the block end cannot miss an escape (u = unit roundoff, eta >= 40u):
+//  * |c| <= 2 - eta: if the computed m_j >= 4 then |z_j|^2 >= 4(1-2u); the computed update obeys
+//    |z_{j+1} - (z_j^2 + c)| <= 5u|z_j|^2, so |z_{j+1}| >= 4(1-7u) - |c| >= 2 + eta - 28u and the
+//    computed m_{j+1} >= 4 + 4 eta - 130u >= 4.  By induction every later m is >= 4 as well.
+//  * |c| >= 2 + eta: z_0 = c and |z_{j+1}| >= |z_j|(|z_j|(1-5u) - 1) >= |z_j| >= |c|, so every
+//    m_j, j >= 1, is >= 4.
+//  * 2 - eta < |c| < 2 + eta (a measure-~0 annulus that does contain grid points such as -2+0i
+//    or 1.2+1.6i): the lane is flagged `risky` and never enters a deferred block.
+// Overflow: before its first escape |z| < 2 (or z = c, |c| <= 2.83), so |z| <= 10.83 at the
+// escape and <= 1.3e133 seven updates later (binary64, K = 8); binary32 allows 3 more updates
+// (|z| <= 2.1e8, m <= 4.4e16... 1.9e33 from the z = c start), hence K = 4.  All values stay
+// finite, so the high-word integer compare remains valid.
+template <typename Real> struct Defer;
+template <> struct Defer<double> {
+    static constexpr int K = 8;
+    static constexpr double kBand = 1.0 / 68719476736.0;      // 2^-36 on |c|^2, i.e. eta = 2^-38 >> 40u
+};
+template <> struct Defer<float> {
+    static constexpr int K = 4;
+    static constexpr float kBand = 1.0f / 512.0f;             // 2^-9 on |c|^2, i.e. eta = 2^-11 >> 40u
+};
+
+template <typename Real>
+__device__ __forceinline__ void update(Real &x, Real &y, Real &xx, Real &yy, Real cr, Real ci)
+{
+    using O = Ops<Real>;
+    const Real t = O::mul(x, y);
+    const Real a = O::sub(xx, yy);
+    y = O::twice_plus(t, ci);
+    x = O::add(a, cr);
+    xx = O::mul(x, x);
+    yy = O::mul(y, y);
+}
+
+// One pixel per lane.  `left` (= mrd-1 updates allowed) is uniform over a tile, so the block
+// structure is warp-uniform; after every block one warp vote lets the whole warp leave as soon as
+// every lane has escaped or hit mrd.  HEAD = number of leading updates that are always tested
+// (pixels that escape early -- most pixels outside the set -- never pay for a replay).
+template <typename Real, int HEAD>
 __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool active)
 {
     using O = Ops<Real>;
+    constexpr int K = Defer<Real>::K;
+    static_assert(HEAD % K == 0, "HEAD must be a multiple of the block size");
     Real x = cr, y = ci;                       // z0 = c  (.py:44-45)
     Real xx = O::mul(x, x), yy = O::mul(y, y);
+    const Real q = O::sub(O::add(xx, yy), (Real)4);
+    const bool risky = (q <= Defer<Real>::kBand) && (q >= -Defer<Real>::kBand);
     int left = mrd - 1;                        // updates still allowed: n = 1 .. mrd-1 (.py:47)
     int n = 0;                                 // updates performed
     int result = 0;                            // 0 = never escaped (.py:68)
     bool done = !active || left <= 0;
     for (;;) {
         if (!done) {
-            if (left >= U) {
-#pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    const Real t = O::mul(x, y);
-                    const Real a = O::sub(xx, yy);
-                    y = O::twice_plus(t, ci);
-                    x = O::add(a, cr);
-                    xx = O::mul(x, x);
-                    yy = O::mul(y, y);
-                    const Real m = O::add(xx, yy);
-                    if (O::escaped(m)) { result = n + j + 1; done = true; break; }
-                }
-                n += U;
-                left -= U;
-                done = done || (left == 0);
-            } else {
+            if (left < K) {
+                // tail: fewer than K updates remain
                 for (; left > 0; --left) {
-                    const Real t = O::mul(x, y);
-                    const Real a = O::sub(xx, yy);
-                    y = O::twice_plus(t, ci);
-                    x = O::add(a, cr);
-                    xx = O::mul(x, x);
-                    yy = O::mul(y, y);
-                    const Real m = O::add(xx, yy);
+                    update<Real>(x, y, xx, yy, cr, ci);
                     ++n;
-                    if (O::escaped(m)) { result = n; break; }
+                    if (O::escaped(O::add(xx, yy))) { result = n; break; }
                 }
                 done = true;
+            } else if (n >= HEAD && !risky) {
+                // steady state: deferred blocks in a tight per-lane loop (no vote inside);
+                // K untested updates, one test, exact replay of the block on escape
+                // The hot loop only DETECTS an escape; the replay happens after it, from the saved
+                // start (sx, sy) of the block that tripped.  Two blocks per trip in explicit SSA
+                // form so that block starts stay live in registers without copies.
+                Real sx = x, sy = y;
+                bool tripped = false;
+                while (left >= 2 * K) {
+                    Real ax = x, ay = y, axx = xx, ayy = yy;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
+                    if (O::escaped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; break; }
+                    Real bx = ax, by = ay, bxx = axx, byy = ayy;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) update<Real>(bx, by, bxx, byy, cr, ci);
+                    if (O::escaped(O::add(bxx, byy))) { sx = ax; sy = ay; n += K; left -= K; tripped = true; break; }
+                    x = bx; y = by; xx = bxx; yy = byy;
+                    n += 2 * K;
+                    left -= 2 * K;
+                }
+                if (!tripped && left >= K) {
+                    Real ax = x, ay = y, axx = xx, ayy = yy;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
+                    if (O::escaped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; }
+                    else { x = ax; y = ay; xx = axx; yy = ayy; n += K; left -= K; }
+                }
+                if (tripped) {
+                    // exact replay of the block that escaped: test after every update (.py:62-66)
+                    x = sx; y = sy;
+                    xx = O::mul(x, x); yy = O::mul(y, y);
+                    for (int j = 1; j <= K; ++j) {
+                        update<Real>(x, y, xx, yy, cr, ci);
+                        if (O::escaped(O::add(xx, yy))) { result = n + j; break; }
+                    }
+                    done = true;
+                }
+                done = done || (left == 0);
+            } else {
+                // head of the orbit (and `risky` lanes): test after every update
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    update<Real>(x, y, xx, yy, cr, ci);
+                    if (O::escaped(O::add(xx, yy))) { result = n + j + 1; done = true; break; }
+                }
+                n += K;
+                left -= K;
+                done = done || (left == 0);
             }
         }
         if (__all_sync(kFull, done)) break;    // warp-vote early-out
@@ -120,18 +198,30 @@ __device__ __forceinline__ double linspace_at(uint32_t k, uint32_t d_minus_1, do
     return (k == d_minus_1) ? stop : __dadd_rn(__dmul_rn((double)k, step), start);
 }
 
+// Where a launch's tile descriptors live: up to kInlineTiles travel inside the kernel parameter
+// block itself (a single-chunk process_workload launch copies nothing at all); larger batches
+// are read from a device array.
+constexpr int kInlineTiles = 4;
+struct TileArgs {
+    const mb_tile *dev;                 // used when n_inline == 0
+    uint32_t n_inline;
+    uint32_t pad;
+    mb_tile inl[kInlineTiles];
+};
+
 // CTA = WX x WY warps; each warp an 8x4 patch.  grid.x = CTAs per tile (row-major over the
 // tile), grid.y = tile index.  OutT = int32_t (counts) or uint8_t (fused .py:96-98 epilogue).
-template <typename Real, typename OutT, int U, int WX, int WY, int MIN_CTAS>
+template <typename Real, typename OutT, int HEAD, int WX, int WY, int MIN_CTAS>
 __global__ void __launch_bounds__(WX * WY * 32, MIN_CTAS)
-escape_tiles_kernel(const mb_tile *__restrict__ tiles, OutT *__restrict__ out)
+escape_tiles_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ out)
 {
     // shared-memory staging of this CTA's tile descriptor (its complex-plane bounds)
     __shared__ mb_tile s_tile;
     static_assert(sizeof(mb_tile) % 8 == 0, "descriptor is copied as 64-bit words");
-    if (threadIdx.x < sizeof(mb_tile) / 8)
-        reinterpret_cast<uint64_t *>(&s_tile)[threadIdx.x] =
-            reinterpret_cast<const uint64_t *>(tiles + blockIdx.y)[threadIdx.x];
+    if (threadIdx.x < sizeof(mb_tile) / 8) {
+        const mb_tile *src = args.n_inline ? &args.inl[blockIdx.y] : args.dev + blockIdx.y;
+        reinterpret_cast<uint64_t *>(&s_tile)[threadIdx.x] = reinterpret_cast<const uint64_t *>(src)[threadIdx.x];
+    }
     __syncthreads();
 
     constexpr uint32_t CW = WX * kWarpW, CH = WY * kWarpH;
@@ -149,7 +239,7 @@ escape_tiles_kernel(const mb_tile *__restrict__ tiles, OutT *__restrict__ out)
     const double ci64 = linspace_at(s_tile.y0 + py, d1, s_tile.start_i, s_tile.step_i, s_tile.stop_i);
     const uint32_t mrd = s_tile.mrd;
 
-    const int res = escape_count<Real, U>(Ops<Real>::coord(cr64), Ops<Real>::coord(ci64), (int)mrd, active);
+    const int res = escape_count<Real, HEAD>(Ops<Real>::coord(cr64), Ops<Real>::coord(ci64), (int)mrd, active);
 
     const size_t row_off = s_tile.out_offset + (size_t)py * s_tile.out_pitch;
     if constexpr (sizeof(OutT) == 4) {
@@ -184,14 +274,14 @@ escape_tiles_kernel(const mb_tile *__restrict__ tiles, OutT *__restrict__ out)
 
 // calc_mb_value as the reference exposes it (.py:39-42,92): explicit coordinate arrays, one
 // thread per element, 32 consecutive elements per warp (the caller chose the order).
-template <typename Real, int U>
-__global__ void __launch_bounds__(128, 16)
+template <typename Real, int HEAD>
+__global__ void __launch_bounds__(128, 12)
 escape_points_kernel(const double *__restrict__ r, const double *__restrict__ i, size_t n, int mrd, int32_t *__restrict__ out)
 {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = k < n;
     const double cr = active ? r[k] : 0.0, ci = active ? i[k] : 0.0;
-    const int res = escape_count<Real, U>(Ops<Real>::coord(cr), Ops<Real>::coord(ci), mrd, active);
+    const int res = escape_count<Real, HEAD>(Ops<Real>::coord(cr), Ops<Real>::coord(ci), mrd, active);
     if (active) out[k] = res;
 }
 

@@ -95,8 +95,9 @@ int check_tiles(const mb_tile *tiles, uint32_t n_tiles, uint32_t *max_w, uint32_
 // Launch shape.  CTA = 2 x 2 warps of 8x4 pixels (16 x 8 pixels, 128 threads): small CTAs
 // release their SM slots soon after their own pixels finish, which matters because escape
 // times differ by orders of magnitude between neighbouring CTAs at the set boundary.
-// <= 32 registers/thread and 16 CTAs/SM = 64 resident warps/SM (full occupancy on sm_100).
-constexpr int kWX = 2, kWY = 2, kMinCtas = 16, kUnroll = 8;
+// <= 40 registers/thread and 12 CTAs/SM = 48 resident warps/SM; the FP64 pipe saturates with
+// ~3 warps per sub-partition, so occupancy beyond that buys nothing.
+constexpr int kWX = 2, kWY = 2, kMinCtas = 12, kHead = 32;
 constexpr uint32_t kCtaW = kWX * mbk::kWarpW, kCtaH = kWY * mbk::kWarpH;
 constexpr uint32_t kMaxGridY = 65535;
 
@@ -111,24 +112,33 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
     DeviceCtx *c = nullptr;
     if ((rc = current_ctx(&c))) return rc;
 
-    // descriptors travel as a stream-ordered device allocation: 88 bytes per tile is the whole
-    // input of the hot path (the reference ships 2 x 128 MiB of float64 per chunk, .py:82-88)
+    // 88 bytes per tile is the whole input of the hot path (the reference ships 2 x 128 MiB of
+    // float64 per chunk, .py:82-88).  Small batches ride in the kernel parameter block; larger
+    // ones in a stream-ordered device allocation (the pool keeps its memory, see mb_init).
+    mbk::TileArgs args;
+    std::memset(&args, 0, sizeof(args));
     mb_tile *tiles_dev = nullptr;
-    const size_t bytes = sizeof(mb_tile) * (size_t)n_tiles;
-    MB_CUDA(cudaMallocAsync((void **)&tiles_dev, bytes, st));
-    MB_CUDA(cudaMemcpyAsync(tiles_dev, tiles, bytes, cudaMemcpyHostToDevice, st));
+    if (n_tiles <= (uint32_t)mbk::kInlineTiles) {
+        args.n_inline = n_tiles;
+        std::memcpy(args.inl, tiles, sizeof(mb_tile) * n_tiles);
+    } else {
+        const size_t bytes = sizeof(mb_tile) * (size_t)n_tiles;
+        MB_CUDA(cudaMallocAsync((void **)&tiles_dev, bytes, st));
+        MB_CUDA(cudaMemcpyAsync(tiles_dev, tiles, bytes, cudaMemcpyHostToDevice, st));
+    }
 
     const uint32_t ctas_per_tile = ((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
     for (uint32_t first = 0; first < n_tiles; first += kMaxGridY) {
         const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
         const dim3 grid(ctas_per_tile, cnt, 1), block(kWX * kWY * 32, 1, 1);
+        args.dev = tiles_dev ? tiles_dev + first : nullptr;
         if (dtype == MB_DTYPE_F64)
-            mbk::escape_tiles_kernel<double, OutT, kUnroll, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(tiles_dev + first, out_dev);
+            mbk::escape_tiles_kernel<double, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
         else
-            mbk::escape_tiles_kernel<float, OutT, kUnroll, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(tiles_dev + first, out_dev);
+            mbk::escape_tiles_kernel<float, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
         MB_CUDA(cudaGetLastError());
     }
-    MB_CUDA(cudaFreeAsync(tiles_dev, st));
+    if (tiles_dev) MB_CUDA(cudaFreeAsync(tiles_dev, st));
     return MB_OK;
 }
 
@@ -182,6 +192,12 @@ int mb_init(int device)
             return fail(MB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         c.sm_count = prop.multiProcessorCount;
         MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        // descriptor batches use cudaMallocAsync: keep the pool's memory across synchronisations
+        // instead of returning it to the OS (default threshold 0 re-allocates on every call)
+        cudaMemPool_t pool;
+        MB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        MB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         c.ready = true;
     }
     g_device = device;
@@ -279,9 +295,9 @@ int mb_calc_mb_value_dev(const double *r_dev, const double *i_dev, size_t n, uin
     const size_t blocks = (n + 127) / 128;
     if (blocks > 0x7fffffffull) return fail(MB_ERR_INVALID, "too many elements for one launch");
     if (dtype == MB_DTYPE_F64)
-        mbk::escape_points_kernel<double, kUnroll><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(r_dev, i_dev, n, (int)mrd, out_dev);
+        mbk::escape_points_kernel<double, kHead><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(r_dev, i_dev, n, (int)mrd, out_dev);
     else
-        mbk::escape_points_kernel<float, kUnroll><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(r_dev, i_dev, n, (int)mrd, out_dev);
+        mbk::escape_points_kernel<float, kHead><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(r_dev, i_dev, n, (int)mrd, out_dev);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

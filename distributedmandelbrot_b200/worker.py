@@ -79,6 +79,82 @@ def process_workload_counts(level: int, mrd: int, index_real: int, index_imag: i
     return out
 
 
+def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, depth: int = 4):
+    """Batch form of process_workload for a list of (level, mrd, index_real, index_imag).
+
+    Same result per workload as process_workload (uint8[definition^2] in HOST memory), but the
+    chunks are pipelined: kernels alternate between two CUDA streams (the tail of chunk k overlaps
+    the head of chunk k+1) and each payload's device->host copy into a pinned ring buffer runs on a
+    third stream behind its kernel.  `consume(workload, payload)` is called in order with a view
+    that is only valid during the call; without `consume` a list of owned arrays is returned.
+    """
+    import torch
+    dev_index = nat.ensure_init()
+    device = torch.device("cuda", dev_index)
+    n = int(definition) * int(definition)
+    workloads = list(workloads)
+    results = [] if consume is None else None
+    if not workloads:
+        return results
+    depth = max(2, min(depth, len(workloads)))
+    ring = _ring(device, n, depth)
+    compute = ring["compute"]
+    copy = ring["copy"]
+    done = [None] * depth                    # copy-finished event per slot
+    tiles = []
+    for (level, mrd, ir, ii) in workloads:
+        _check_u32(level=level, mrd=mrd, index_real=ir, index_imag=ii, definition=definition)
+        tiles.append(nat.chunk_geometry(level, ir, ii, definition, mrd))
+    lib = nat.lib()
+
+    def finish(k):
+        slot = k % depth
+        done[slot].synchronize()
+        payload = ring["host_np"][slot]
+        if consume is None:
+            results.append(payload.copy())
+        else:
+            consume(workloads[k], payload)
+
+    for k, t in enumerate(tiles):
+        slot = k % depth
+        if k >= depth:
+            finish(k - depth)                # frees this slot's host and device buffers
+        st = compute[k % len(compute)]
+        nat.check(lib.mb_render_u8(C.byref(t), 1, ring["dev"][slot].data_ptr(), nat.DTYPE_F64, st.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(st)
+        copy.wait_event(ev)
+        with torch.cuda.stream(copy):
+            ring["host"][slot].copy_(ring["dev"][slot], non_blocking=True)
+        done[slot] = torch.cuda.Event()
+        done[slot].record(copy)
+        # (the kernel that reuses this slot, k + depth, is only launched after finish(k) has
+        #  synchronised on done[slot], so no extra stream dependency is needed)
+    for k in range(max(0, len(tiles) - depth), len(tiles)):
+        finish(k)
+    return results
+
+
+_RINGS = {}
+
+
+def _ring(device, n: int, depth: int):
+    """Pinned host + device payload ring and the streams of process_workloads (cached per shape)."""
+    import torch
+    key = (device.index, n, depth)
+    r = _RINGS.get(key)
+    if r is None:
+        _RINGS.clear()                       # one shape at a time: the buffers are 16 MiB each
+        host = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        r = {"host": host, "host_np": [h.numpy() for h in host],
+             "dev": [torch.empty(n, dtype=torch.uint8, device=device) for _ in range(depth)],
+             "compute": [torch.cuda.Stream(device), torch.cuda.Stream(device)],
+             "copy": torch.cuda.Stream(device)}
+        _RINGS[key] = r
+    return r
+
+
 def calc_mb_value(r, i, mrd: int, out: np.ndarray | None = None) -> np.ndarray:
     """(.py:39-68) element-wise escape count over explicit coordinate arrays, like the
     reference's numba ufunc `int32(float64, float64, int32)`.  r and i broadcast together."""

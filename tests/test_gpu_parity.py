@@ -146,6 +146,41 @@ def test_calc_mb_value_points(gpu, oracle):
     assert g.shape == (5, 7)
 
 
+def test_every_mrd_around_the_block_boundaries(gpu, oracle):
+    """The kernel tests every update for the first HEAD = 32 updates, then runs untested blocks of
+    K = 8 (f64) / 4 (f32) with an exact replay, then a tested tail: sweep mrd across all of those
+    boundaries on a tile that straddles the set boundary."""
+    from distributedmandelbrot_b200 import worker
+    level, ir, ii, d = 10, 3, 5, 64
+    for dtype in ("f64", "f32"):
+        for mrd in list(range(0, 84)) + [95, 96, 97, 127, 128, 129, 130, 255, 1000, 1001, 1003]:
+            got = worker.process_workload_counts(level, mrd, ir, ii, definition=d, dtype=dtype).reshape(d, d)
+            want = oracle.render_chunk_counts(level, mrd, ir, ii, d, dtype=dtype)
+            assert np.array_equal(got, want), (dtype, mrd)
+
+
+def test_points_on_the_radius_2_circle(gpu, oracle):
+    """|c| ~= 2 is the one place where "escaped stays escaped" is not provable from rounding
+    bounds; such lanes are flagged and take the test-every-update path.  Grid points like -2+0i or
+    1.2+1.6i do occur in DataChunks."""
+    from distributedmandelbrot_b200 import worker
+    rng = np.random.default_rng(11)
+    th = np.concatenate([rng.uniform(0, 2 * np.pi, 4000), np.linspace(np.pi - 1e-6, np.pi + 1e-6, 2001)])
+    rad = 2.0 + np.concatenate([rng.choice([0.0, 1e-16, -1e-16, 4e-16, -4e-16, 1e-13, -1e-13, 1e-11, -1e-11, 2e-11, -2e-11, 1e-9, -1e-9], th.size)])
+    r = np.concatenate([[-2.0, 2.0, 0.0, 0.0, 1.2, 1.6, -1.2, -1.6, 1.2, -2.0, -2.0, -1.9999999999999998],
+                        rad * np.cos(th)])
+    i = np.concatenate([[0.0, 0.0, 2.0, -2.0, 1.6, 1.2, 1.6, -1.2, -1.6, 5e-324, 1e-17, 0.0],
+                        rad * np.sin(th)])
+    for mrd in (2, 33, 41, 500, 5000):
+        got = worker.calc_mb_value(r, i, mrd)
+        want = np.array([oracle.escape_f64(a, b, mrd) for a, b in zip(r, i)], np.int32)
+        assert np.array_equal(got, want), mrd
+    # chunks whose corner/edge lies on the circle: level 1 (corners at +-2), level 5 (1.2 / 1.6 grid lines)
+    for (level, ir, ii, d, mrd) in [(1, 0, 0, 129, 300), (2, 0, 1, 65, 300), (5, 4, 4, 101, 200), (5, 0, 4, 201, 200)]:
+        got = worker.process_workload_counts(level, mrd, ir, ii, definition=d).reshape(d, d)
+        assert np.array_equal(got, oracle.render_chunk_counts(level, mrd, ir, ii, d)), (level, ir, ii)
+
+
 def test_u8_epilogue_standalone_and_fused(gpu, golden_meta, golden_arrays):
     import torch
     for rec in golden_meta["u8"]:
