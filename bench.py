@@ -97,10 +97,8 @@ def cpu_sample(spec, d: int, threads: int):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     t0 = time.perf_counter()
-    useful = 0
-    for (ir, ii) in spec.chunk_indices():
-        c = oracle.render_chunk_counts(spec.level, spec.mrd, ir, ii, d, dtype=spec.dtype, threads=threads)
-        useful += oracle.useful_iterations(c, spec.mrd)
+    _counts, useful = oracle.render_frame(spec.level, spec.ir0, spec.ii0, spec.blocks, d, spec.mrd,
+                                          dtype=spec.dtype, threads=threads, want_counts=False)
     return useful, time.perf_counter() - t0
 
 
@@ -117,7 +115,7 @@ def cpu_baseline(spec, budget_s: float = 15.0):
     return {"value": useful / sec / 1e9, "unit": METRIC, "cores": threads, "kind": "port",
             "sample": f"same frame ({spec.name}), all {spec.n_chunks} chunks at reduced definition d={d} "
                       f"({useful:.4g} pixel-iterations in {sec:.1f} s); oracle/mandel_oracle.c, gcc -O2 -ffp-contract=off, "
-                      f"{threads} pthreads"}, d
+                      f"{threads} pthreads, one dynamic (chunk,row) queue"}, d
 
 
 def run_reference(args, spec):

@@ -216,6 +216,78 @@ int mbo_process_workload(uint32_t level, int32_t mrd, uint32_t index_real, uint3
     return rc;
 }
 
+/* ---- whole-frame driver for the CPU baseline: ONE dynamic queue over every (chunk, row) of a
+ * blocks x blocks frame, so that all host cores stay busy (per-chunk calls leave cores idle at
+ * small definitions).  Same per-pixel code path as mbo_render_rect. ---------------------------- */
+typedef struct {
+    uint32_t level, ir0, ii0, blocks, d;
+    int32_t mrd;
+    int dtype;
+    int32_t *out;                 /* may be NULL: only the useful-iteration sum is wanted */
+    atomic_ullong next;           /* next (chunk * d + row) item */
+    atomic_ullong useful;
+} mbo_frame_job;
+
+static void *mbo_frame_worker(void *arg)
+{
+    mbo_frame_job *j = (mbo_frame_job *)arg;
+    const uint32_t d = j->d;
+    const uint64_t items = (uint64_t)j->blocks * j->blocks * d;
+    double *r = (double *)malloc(sizeof(double) * d);
+    double *im = (double *)malloc(sizeof(double) * d);
+    int32_t *rowbuf = (int32_t *)malloc(sizeof(int32_t) * d);
+    if (!r || !im || !rowbuf) { free(r); free(im); free(rowbuf); return NULL; }
+    uint64_t have_chunk = UINT64_MAX, local = 0;
+    const uint64_t never = j->mrd > 0 ? (uint64_t)(j->mrd - 1) : 0;
+    for (;;) {
+        const uint64_t it = atomic_fetch_add(&j->next, 1ull);
+        if (it >= items) break;
+        const uint64_t chunk = it / d;
+        const uint32_t row = (uint32_t)(it % d);
+        if (chunk != have_chunk) {
+            /* chunk order as in the product's frame layout: chunk = bi * blocks + br */
+            const uint32_t bi = (uint32_t)(chunk / j->blocks), br = (uint32_t)(chunk % j->blocks);
+            double range, sr, si;
+            mbo_chunk_geometry(j->level, j->ir0 + br, j->ii0 + bi, &range, &sr, &si);
+            volatile double stop_r = sr + range, stop_i = si + range;
+            mbo_linspace(sr, stop_r, d, r);
+            mbo_linspace(si, stop_i, d, im);
+            have_chunk = chunk;
+        }
+        int32_t *o = j->out ? j->out + (size_t)it * d : rowbuf;
+        const double ci = im[row];
+        if (j->dtype == 0) {
+            for (uint32_t col = 0; col < d; ++col) o[col] = mbo_escape_f64(r[col], ci, j->mrd);
+        } else {
+            const float cif = (float)ci;
+            for (uint32_t col = 0; col < d; ++col) o[col] = mbo_escape_f32((float)r[col], cif, j->mrd);
+        }
+        for (uint32_t col = 0; col < d; ++col) local += o[col] ? (uint64_t)o[col] : never;
+    }
+    atomic_fetch_add(&j->useful, local);
+    free(r); free(im); free(rowbuf);
+    return NULL;
+}
+
+int mbo_render_frame(uint32_t level, uint32_t ir0, uint32_t ii0, uint32_t blocks, uint32_t d,
+                     int32_t mrd, int dtype, int threads, int32_t *out, uint64_t *useful)
+{
+    if (level == 0 || d == 0 || blocks == 0) return -1;
+    if (dtype != 0 && dtype != 1) return -2;
+    mbo_frame_job job = {level, ir0, ii0, blocks, d, mrd, dtype, out, 0, 0};
+    int nt = threads > 0 ? threads : mbo_max_threads();
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nt);
+    int started = 0;
+    if (th)
+        for (; started < nt - 1; ++started)
+            if (pthread_create(&th[started], NULL, mbo_frame_worker, &job) != 0) break;
+    mbo_frame_worker(&job);
+    for (int k = 0; k < started; ++k) pthread_join(th[k], NULL);
+    free(th);
+    if (useful) *useful = (uint64_t)atomic_load(&job.useful);
+    return 0;
+}
+
 uint64_t mbo_useful_iterations(const int32_t *counts, size_t n, int32_t mrd)
 {
     uint64_t s = 0;

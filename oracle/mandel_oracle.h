@@ -61,6 +61,14 @@ int mbo_process_workload(uint32_t level, int32_t mrd, uint32_t index_real, uint3
                          uint32_t d, uint8_t *out_u8, int32_t *out_counts /* may be NULL */,
                          int threads);
 
+/*
+ * A blocks x blocks frame of chunks (ir0+br, ii0+bi) at `level`, definition d, threaded over all
+ * (chunk, row) items with one dynamic queue.  out (may be NULL) is chunk-contiguous
+ * [bi*blocks+br][row][col]; *useful receives the sum of (n ? n : mrd-1).  Used by the CPU baseline.
+ */
+int mbo_render_frame(uint32_t level, uint32_t ir0, uint32_t ii0, uint32_t blocks, uint32_t d,
+                     int32_t mrd, int dtype, int threads, int32_t *out, uint64_t *useful);
+
 void mbo_counts_to_u8(const int32_t *counts, uint8_t *out, size_t n, int32_t mrd);
 
 /* sum over pixels of (n ? n : mrd-1): the unit of the Gpixel-iterations/s metric */

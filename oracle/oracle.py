@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
         L.mbo_render_rect.restype = C.c_int
         L.mbo_process_workload.argtypes = [u32, i32, u32, u32, u32, pu8, pi32, C.c_int]
         L.mbo_process_workload.restype = C.c_int
+        L.mbo_render_frame.argtypes = [u32, u32, u32, u32, u32, i32, C.c_int, C.c_int, pi32, C.POINTER(u64)]
+        L.mbo_render_frame.restype = C.c_int
         L.mbo_counts_to_u8.argtypes = [pi32, pu8, sz, i32]
         L.mbo_counts_to_u8.restype = None
         L.mbo_useful_iterations.argtypes = [pi32, sz, i32]
@@ -112,6 +114,17 @@ def process_workload(level, mrd, index_real, index_imag, d=4096, threads=0, want
     if rc != 0:
         raise ValueError(f"mbo_process_workload failed rc={rc}")
     return (out, counts) if want_counts else out
+
+
+def render_frame(level, ir0, ii0, blocks, d, mrd, dtype="f64", threads=0, want_counts=True):
+    """Whole frame on all cores -> (counts[blocks*blocks, d, d] or None, useful pixel-iterations)."""
+    out = np.empty((blocks * blocks, d, d), dtype=np.int32) if want_counts else None
+    useful = C.c_uint64()
+    rc = lib().mbo_render_frame(level, ir0, ii0, blocks, d, mrd, {"f64": 0, "f32": 1}[dtype], threads,
+                                _p(out, C.c_int32) if want_counts else None, C.byref(useful))
+    if rc != 0:
+        raise ValueError(f"mbo_render_frame failed rc={rc}")
+    return out, int(useful.value)
 
 
 def counts_to_u8(counts: np.ndarray, mrd: int) -> np.ndarray:

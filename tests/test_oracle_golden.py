@@ -110,3 +110,13 @@ def test_edge_semantics(oracle):
     assert oracle.escape_f64(3.0, 0.0, 1) == 0          # mrd = 1: range(1, 1) is empty
     assert oracle.escape_f64(3.0, 0.0, 2) == 1
     assert oracle.useful_iterations(np.array([0, 1, 5, 0], np.int32), 10) == 9 + 1 + 5 + 9
+
+
+def test_frame_driver_equals_per_chunk(oracle):
+    """The CPU baseline's whole-frame driver is the same per-pixel path, threaded differently."""
+    counts, useful = oracle.render_frame(10, 2, 4, 3, 40, 200)
+    for k, (ir, ii) in enumerate([(2 + br, 4 + bi) for bi in range(3) for br in range(3)]):
+        assert np.array_equal(counts[k], oracle.render_chunk_counts(10, 200, ir, ii, 40))
+    assert useful == oracle.useful_iterations(counts, 200)
+    c32, _ = oracle.render_frame(4, 1, 1, 2, 33, 300, dtype="f32")
+    assert np.array_equal(c32[3], oracle.render_chunk_counts(4, 300, 2, 2, 33, dtype="f32"))
