@@ -86,6 +86,7 @@ SIGNATURES = {
     "mb_wsq_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
     "mb_wsq_reset": (_int, [_vp, _u32]),
     "mb_wsq_pop": (_int, [_vp, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "mb_wsq_remaining": (C.c_int64, [_vp]),
     "mb_wsq_close": (_int, [_vp]),
     "mb_wsq_unlink": (_int, [C.c_char_p]),
     "mb_measure_fma_peak": (_int, [_int, _int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
@@ -191,6 +192,9 @@ class TileQueue:
         if rc == 0:
             return None
         return first.value, got.value, bool(stolen.value)
+
+    def remaining(self) -> int:
+        return int(check(lib().mb_wsq_remaining(self._h)))
 
     def close(self) -> None:
         if self._h:

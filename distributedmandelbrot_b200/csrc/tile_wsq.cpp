@@ -204,6 +204,12 @@ int mb_wsq_pop(mb_wsq *q, uint32_t rank, uint32_t want, uint32_t *first, uint32_
     }
 }
 
+int64_t mb_wsq_remaining(mb_wsq *q)
+{
+    if (!q) return qfail(MB_ERR_INVALID, "NULL queue");
+    return (int64_t)__atomic_load_n(&q->sh->remaining, __ATOMIC_ACQUIRE);
+}
+
 int mb_wsq_close(mb_wsq *q)
 {
     if (!q) return MB_OK;

@@ -139,7 +139,9 @@ class FrameRenderer:
         inflight = []
         cuda = self.device.type == "cuda"
         while True:
-            got = queue.pop(self.rank, self.bands_per_claim)
+            # guided self-scheduling: full-size claims while plenty is left, single bands at the end
+            want = max(1, min(self.bands_per_claim, queue.remaining() // (self.world * 8)))
+            got = queue.pop(self.rank, want)
             if got is None:
                 break
             first, cnt, stolen = got

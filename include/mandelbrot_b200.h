@@ -189,6 +189,8 @@ int mb_wsq_reset(mb_wsq *q, uint32_t total);
  */
 int mb_wsq_pop(mb_wsq *q, uint32_t rank, uint32_t want, uint32_t *first, uint32_t *got,
                uint32_t *stolen);
+/* indices not yet handed out (all ranks); lets callers shrink their claims near the end */
+int64_t mb_wsq_remaining(mb_wsq *q);
 int mb_wsq_close(mb_wsq *q);
 int mb_wsq_unlink(const char *name);
 
