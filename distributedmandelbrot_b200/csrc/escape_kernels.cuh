@@ -76,17 +76,22 @@ template <> struct Ops<float> {
 //  * 2 - eta < |c| < 2 + eta (a measure-~0 annulus that does contain grid points such as -2+0i
 //    or 1.2+1.6i): the lane is flagged `risky` and never enters a deferred block.
 // Overflow: before its first escape |z| < 2 (or z = c, |c| <= 2.83), so |z| <= 10.83 at the
-// escape and <= 1.3e133 seven updates later (binary64, K = 8); binary32 allows 3 more updates
-// (|z| <= 2.1e8, m <= 4.4e16... 1.9e33 from the z = c start), hence K = 4.  All values stay
-// finite, so the high-word integer compare remains valid.
+// escape and <= 1.3e133 seven updates later: with K = 8 every binary64 value stays finite and the
+// block-end test can stay an integer compare of m's high word.  binary32 would overflow after 4
+// more updates, so its block-end test is `!(m < 4)` instead: once a value overflows it can only
+// become +-inf or NaN and stays that way through every later mul/add/fma, and both make
+// `!(m < 4)` true -- which allows K = 16 (the FP32 pipe issues one instruction per cycle, so the
+// loop overhead per block matters twice as much as in binary64).
 template <typename Real> struct Defer;
 template <> struct Defer<double> {
     static constexpr int K = 8;
     static constexpr double kBand = 1.0 / 68719476736.0;      // 2^-36 on |c|^2, i.e. eta = 2^-38 >> 40u
+    static __device__ __forceinline__ bool tripped(double m) { return __double2hiint(m) >= 0x40100000; }
 };
 template <> struct Defer<float> {
-    static constexpr int K = 4;
+    static constexpr int K = 16;
     static constexpr float kBand = 1.0f / 512.0f;             // 2^-9 on |c|^2, i.e. eta = 2^-11 >> 40u
+    static __device__ __forceinline__ bool tripped(float m) { return !(m < 4.0f); }
 };
 
 template <typename Real>
@@ -141,11 +146,11 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
                     Real ax = x, ay = y, axx = xx, ayy = yy;
 #pragma unroll
                     for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
-                    if (O::escaped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; break; }
+                    if (Defer<Real>::tripped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; break; }
                     Real bx = ax, by = ay, bxx = axx, byy = ayy;
 #pragma unroll
                     for (int j = 0; j < K; ++j) update<Real>(bx, by, bxx, byy, cr, ci);
-                    if (O::escaped(O::add(bxx, byy))) { sx = ax; sy = ay; n += K; left -= K; tripped = true; break; }
+                    if (Defer<Real>::tripped(O::add(bxx, byy))) { sx = ax; sy = ay; n += K; left -= K; tripped = true; break; }
                     x = bx; y = by; xx = bxx; yy = byy;
                     n += 2 * K;
                     left -= 2 * K;
@@ -154,7 +159,7 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
                     Real ax = x, ay = y, axx = xx, ayy = yy;
 #pragma unroll
                     for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
-                    if (O::escaped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; }
+                    if (Defer<Real>::tripped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; }
                     else { x = ax; y = ay; xx = axx; yy = ayy; n += K; left -= K; }
                 }
                 if (tripped) {

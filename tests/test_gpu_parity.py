@@ -274,3 +274,20 @@ def test_full_size_chunk_properties(gpu, oracle):
     for y in rows:
         want = oracle.render_chunk_counts(spec.level, 10000, ir, ii, d, x0=0, y0=y, w=d, h=1)
         assert np.array_equal(a.reshape(d, d)[y], want[0]), y
+
+
+def test_process_workloads_pipeline_equals_single_calls(gpu, oracle):
+    """The batched/pipelined worker entry point returns exactly what process_workload returns."""
+    from distributedmandelbrot_b200 import worker
+    wl = [(10, 300, 3, 5), (4, 64, 0, 0), (16, 500, 5, 8), (10, 300, 4, 5), (8, 100, 3, 4), (3, 200, 1, 1), (2, 50, 1, 0)]
+    d = 192
+    got = worker.process_workloads(wl, definition=d, depth=3)
+    assert len(got) == len(wl)
+    for w, g in zip(wl, got):
+        assert g.dtype == np.uint8 and g.shape == (d * d,)
+        assert np.array_equal(g, worker.process_workload(*w, definition=d)), w
+        assert np.array_equal(g, oracle.process_workload(*w, d)), w
+    seen = []
+    worker.process_workloads(wl[:2], definition=d, consume=lambda w, p: seen.append((w, int(p.sum()))))
+    assert [s[0] for s in seen] == wl[:2] and seen[0][1] == int(got[0].sum())
+    assert worker.process_workloads([], definition=d) == []
