@@ -42,6 +42,8 @@ def get_spec(name: str):
         return CONFIGS[name]
     if name == "cfg4_4x4":      # 4x4 chunk sub-block of cfg4 around the zoom centre (for ncu --set full captures)
         return CONFIGS["cfg4"].scaled(name="cfg4 4x4 sub-block at (248,418)", blocks=4, ir0=248, ii0=418)
+    if name == "cfg3_1":        # one 4096^2 chunk of cfg3 straddling the set (for the FP32 ncu capture)
+        return CONFIGS["cfg3"].scaled(name="cfg3 single chunk (1,1)", blocks=1, ir0=1, ii0=1)
     if name == "cfg4_1":
         return CONFIGS["cfg4"].scaled(name="cfg4 single interior chunk (242,412)", blocks=1)
     raise SystemExit(f"unknown workload {name}")
@@ -246,27 +248,55 @@ def main() -> None:
     ms_per_step = total_ms / args.steps
 
     # ---- e2e: the reference-facing worker API with HOST buffers (rank-local share of the chunks)
-    e2e = None
+    # chunks are handed out dynamically by a second work-stealing queue, the way a Distributer
+    # hands leases to whichever worker asks next
     chunks = spec.chunk_indices()
-    mine = chunks[rank::world]
+    wl_all = [(spec.level, spec.mrd, ir, ii) for (ir, ii) in chunks]
+    e2e_s = None
     if spec.dtype == "f64" and args.e2e_steps > 0:
-        wl = [(spec.level, spec.mrd, ir, ii) for (ir, ii) in mine]
-        worker.process_workloads(wl[:2], definition=spec.definition, consume=lambda *_: None)   # warm the pinned ring
+        cq = None
         if world > 1:
+            cqn = queue_name() + "_c"
+            if rank == 0:
+                cq = nat.TileQueue(cqn, world, len(wl_all), create=True)
             dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+            if rank != 0:
+                cq = nat.TileQueue(cqn)
+
+        def source():
+            if cq is None:
+                yield from wl_all
+                return
+            while (g := cq.pop(rank, 1)) is not None:
+                for k in range(g[0], g[0] + g[1]):
+                    yield wl_all[k]
+
+        worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None)   # warm the pinned ring
+        total_s = 0.0
         nbytes = 0
+
+        def consume(_w, payload):
+            nonlocal nbytes
+            nbytes += payload.nbytes
+
         for _ in range(args.e2e_steps):
-            def consume(_w, payload):
-                nonlocal nbytes
-                nbytes += payload.nbytes
-            worker.process_workloads(wl, definition=spec.definition, consume=consume)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_s = float(dt.item()) / args.e2e_steps
+            if world > 1:
+                dist.barrier()
+                if rank == 0:
+                    cq.reset(len(wl_all))
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            worker.process_workloads(source(), definition=spec.definition, consume=consume)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)       # max over ranks, per step
+            total_s += float(dt.item())
+        e2e_s = total_s / args.e2e_steps
+        if cq is not None:
+            dist.barrier()
+            cq.close()
 
     if rank == 0:
         value = useful / (ms_per_step * 1e-3) / 1e9

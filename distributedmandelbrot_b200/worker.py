@@ -87,39 +87,39 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
     the head of chunk k+1) and each payload's device->host copy into a pinned ring buffer runs on a
     third stream behind its kernel.  `consume(workload, payload)` is called in order with a view
     that is only valid during the call; without `consume` a list of owned arrays is returned.
+    `workloads` may be any iterable and is consumed lazily (e.g. a generator that pops chunk
+    indices from the in-box work-stealing queue, or one that asks a Distributer for the next lease).
     """
     import torch
     dev_index = nat.ensure_init()
     device = torch.device("cuda", dev_index)
     n = int(definition) * int(definition)
-    workloads = list(workloads)
     results = [] if consume is None else None
-    if not workloads:
-        return results
-    depth = max(2, min(depth, len(workloads)))
+    depth = max(2, int(depth))
     ring = _ring(device, n, depth)
     compute = ring["compute"]
     copy = ring["copy"]
     done = [None] * depth                    # copy-finished event per slot
-    tiles = []
-    for (level, mrd, ir, ii) in workloads:
-        _check_u32(level=level, mrd=mrd, index_real=ir, index_imag=ii, definition=definition)
-        tiles.append(nat.chunk_geometry(level, ir, ii, definition, mrd))
+    pending = [None] * depth                 # workload whose payload sits in the slot
     lib = nat.lib()
 
-    def finish(k):
-        slot = k % depth
+    def finish(slot):
         done[slot].synchronize()
         payload = ring["host_np"][slot]
         if consume is None:
             results.append(payload.copy())
         else:
-            consume(workloads[k], payload)
+            consume(pending[slot], payload)
+        pending[slot] = None
 
-    for k, t in enumerate(tiles):
+    k = 0
+    for w in workloads:                      # consumed lazily: the source may be a live queue
+        level, mrd, ir, ii = w
+        _check_u32(level=level, mrd=mrd, index_real=ir, index_imag=ii, definition=definition)
+        t = nat.chunk_geometry(level, ir, ii, definition, mrd)
         slot = k % depth
-        if k >= depth:
-            finish(k - depth)                # frees this slot's host and device buffers
+        if pending[slot] is not None:
+            finish(slot)                     # frees this slot's host and device buffers
         st = compute[k % len(compute)]
         nat.check(lib.mb_render_u8(C.byref(t), 1, ring["dev"][slot].data_ptr(), nat.DTYPE_F64, st.cuda_stream))
         ev = torch.cuda.Event()
@@ -129,10 +129,11 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
             ring["host"][slot].copy_(ring["dev"][slot], non_blocking=True)
         done[slot] = torch.cuda.Event()
         done[slot].record(copy)
-        # (the kernel that reuses this slot, k + depth, is only launched after finish(k) has
-        #  synchronised on done[slot], so no extra stream dependency is needed)
-    for k in range(max(0, len(tiles) - depth), len(tiles)):
-        finish(k)
+        pending[slot] = w
+        k += 1
+    for j in range(k, k + depth):            # drain in submission order
+        if pending[j % depth] is not None:
+            finish(j % depth)
     return results
 
 
@@ -257,6 +258,32 @@ def do_workload_single(addr: str, port: int, *, verbose: bool = True) -> bool:
     return True
 
 
+def run_pipelined(addr: str, port: int, *, depth: int = 4, verbose: bool = True) -> int:
+    """Same protocol as looping do_workload_single, but several leases in flight:
+    while chunk k computes, chunk k+1.. are already leased and queued on the GPU and chunk k-1 is
+    being sent back.  Each exchange still uses its own short connection (Distributer.cs:230-274)
+    and nothing is held open during compute.  Returns the number of workloads processed."""
+    say = print if verbose else (lambda *a, **k: None)
+    count = 0
+
+    def leases():
+        while True:
+            w = request_workload(addr, port)
+            if w is None:
+                say("No workload was available, ending program")
+                return
+            say("Workload received:", w)
+            yield w
+
+    def send_back(w, payload):
+        nonlocal count
+        count += 1
+        say("Sent response" if return_workload(addr, port, w, payload) else "Response rejected", w)
+
+    process_workloads(leases(), consume=send_back, depth=depth)
+    return count
+
+
 def main(argv=None) -> None:
     """(.py:178-184) prompts `Server Addr> ` / `Server Port> ` like the reference; --addr/--port/
     --device skip the prompts."""
@@ -265,10 +292,15 @@ def main(argv=None) -> None:
     ap.add_argument("--addr")
     ap.add_argument("--port", type=int)
     ap.add_argument("--device", type=int, default=None)
+    ap.add_argument("--pipeline", type=int, default=0, metavar="DEPTH",
+                    help="keep DEPTH leases in flight (0 = one at a time, like the reference)")
     args = ap.parse_args(argv)
     addr = args.addr if args.addr is not None else input("Server Addr> ")
     port = args.port if args.port is not None else int(input("Server Port> "))
     nat.ensure_init(args.device)
+    if args.pipeline > 0:
+        run_pipelined(addr, port, depth=max(2, args.pipeline))
+        return
     while do_workload_single(addr, port):
         pass
 

@@ -59,6 +59,19 @@ def test_protocol_end_to_end_on_gpu(gpu, oracle):
     _check_session(oracle, fd, n, wl, {wl[0]})
 
 
+@pytest.mark.gpu
+def test_pipelined_worker_on_gpu(gpu, oracle):
+    """Several leases in flight (row f4): same bytes on the wire, every workload exactly once."""
+    from distributedmandelbrot_b200 import worker
+    wl = [(4, 8, 0, 0), (4, 8, 3, 0), (4, 6, 0, 3), (4, 64, 1, 2), (4, 8, 3, 3), (4, 9, 0, 1), (4, 7, 2, 0)]
+    fd = FakeDistributer(wl, reject=[wl[2]])
+    try:
+        n = worker.run_pipelined("127.0.0.1", fd.port, depth=3, verbose=False)
+    finally:
+        fd.close()
+    _check_session(oracle, fd, n, wl, {wl[2]})
+
+
 def test_workload_record_is_16_le_bytes():
     """SURVEY.md Appendix B.1 example: (level=4, mrd=256, ir=1, ii=2)."""
     import socket
