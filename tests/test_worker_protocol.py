@@ -18,10 +18,13 @@ def _run_worker(worker, port):
     return n
 
 
-def _check_session(oracle, fd, n_done, workloads, rejected):
+def _check_session(oracle, fd, n_done, workloads, rejected, pipelined=False):
     assert fd.error is None, fd.error
     assert n_done == len(workloads)
-    assert fd.log[-1] == ("none",)                                   # 0x11 ended the loop
+    if pipelined:
+        assert fd.log.count(("none",)) == 1                          # leases run ahead of the responses
+    else:
+        assert fd.log[-1] == ("none",)                               # 0x11 ended the loop
     for w in workloads:
         if w in rejected:
             assert ("reject", w) in fd.log and w not in fd.completed
@@ -69,7 +72,7 @@ def test_pipelined_worker_on_gpu(gpu, oracle):
         n = worker.run_pipelined("127.0.0.1", fd.port, depth=3, verbose=False)
     finally:
         fd.close()
-    _check_session(oracle, fd, n, wl, {wl[2]})
+    _check_session(oracle, fd, n, wl, {wl[2]}, pipelined=True)
 
 
 def test_workload_record_is_16_le_bytes():
