@@ -80,6 +80,10 @@ SIGNATURES = {
     "mb_counts_to_u8": (_int, [_vp, _vp, _sz, _u32, _vp]),
     "mb_useful_iterations": (_int, [_vp, _sz, _u32, _vp, _vp]),
     "mb_classify_u8": (_int, [_vp, _sz, _vp, _vp]),
+    "mb_serialize_workspace_bytes": (_sz, [_sz]),
+    "mb_serialize_chunk": (_int, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "mb_serialize_chunk_host": (_int, [_vp, _sz, _vp, _sz, C.POINTER(_u64)]),
+    "mb_process_workload_serialized": (_int, [_u32, _u32, _u32, _u32, _u32, _vp, _sz, C.POINTER(_u64), C.POINTER(_i32)]),
     "mb_process_workload_u8": (_int, [_u32, _u32, _u32, _u32, _u32, _vp]),
     "mb_process_workload_counts": (_int, [_u32, _u32, _u32, _u32, _u32, _int, _vp]),
     "mb_wsq_create": (_int, [C.c_char_p, _u32, _u32, C.POINTER(_vp)]),

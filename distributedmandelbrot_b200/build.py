@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libmandelbrot_b200.so")
 SOURCES = ["mandelbrot_capi.cu", "tile_wsq.cpp"]
-HEADERS = ["escape_kernels.cuh", os.path.join("..", "..", "include", "mandelbrot_b200.h")]
+HEADERS = ["escape_kernels.cuh", "chunk_codec.cuh", os.path.join("..", "..", "include", "mandelbrot_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

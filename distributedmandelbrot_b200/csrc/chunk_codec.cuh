@@ -1,0 +1,174 @@
+// chunk_codec.cuh -- DataChunk serialisation on the device, HBM-bound byte work.
+//
+// Replaces DataChunk.Serialize (DistributedMandelbrot/DataChunk.cs:173-206), which serialises the
+// 16 MiB payload TWICE on one CPU thread (RawSerializer, DataChunkSerializer.cs:29-49, and
+// RLESerializer, :51-100, each into a SizeCountStream) to pick the shorter and then a third time
+// to write it.  Output bytes are identical to the reference's:
+//     byte 0 = codec: 0x00 raw -> the n payload bytes ; 0x01 RLE -> (uint32 LE runLength, uint8
+//     value) records, one per maximal run.  Raw wins ties (`<` with Raw first, DataChunk.cs:188).
+//
+// Four small kernels; every pass is a coalesced 128-bit stream over the payload:
+//   1 count_run_starts   per-CTA number of run starts (p[i] != p[i-1], i = 0 always starts a run)
+//   2 scan_block_counts  exclusive scan of the CTA counts, picks the codec, writes header + length
+//   3 scatter_runs       RLE: every run start -> starts[r], value byte into its record
+//                        raw: the payload copied behind the header byte (byte-shifted words)
+//   4 write_run_lengths  RLE: runLength = starts[r+1] - starts[r] into the records
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mbc {
+
+constexpr int kThreads = 256;
+constexpr int kBytesPerThread = 16;
+constexpr int kSegment = kThreads * kBytesPerThread;   // 4096 payload bytes per CTA
+
+struct Meta {
+    unsigned long long out_len;   // total serialised bytes, header included
+    uint32_t runs;
+    uint32_t codec;               // 0 raw, 1 RLE
+};
+
+// 16-bit mask: bit j set iff byte j of this thread's 16-byte span starts a run
+__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint8_t *bytes)
+{
+    uint32_t mask = 0;
+    if (base >= n) return 0;
+    const bool full = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0);
+    if (full) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+        reinterpret_cast<uint4 *>(bytes)[0] = v;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kBytesPerThread; ++j) bytes[j] = (base + j < n) ? p[base + j] : 0;
+    }
+    uint8_t prev = base ? p[base - 1] : 0;
+#pragma unroll
+    for (int j = 0; j < kBytesPerThread; ++j) {
+        if (base + j < n && (base + j == 0 || bytes[j] != prev)) mask |= 1u << j;
+        prev = bytes[j];
+    }
+    return mask;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[kThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        const uint32_t s = warp_sums[w];
+        if ((uint32_t)w < warp) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kThreads) count_run_starts(const uint8_t *__restrict__ p, size_t n, uint32_t *__restrict__ block_counts)
+{
+    alignas(16) uint8_t bytes[kBytesPerThread];
+    const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
+    const uint32_t c = __popc(start_mask(p, base, n, bytes));
+    uint32_t total;
+    block_exclusive_scan(c, &total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// one CTA; in-place exclusive scan of block_counts[0..nblocks)
+__global__ void __launch_bounds__(kThreads) scan_block_counts(uint32_t *__restrict__ block_counts, uint32_t nblocks, size_t n,
+                                                             Meta *__restrict__ meta, uint8_t *__restrict__ out)
+{
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t first = 0; first < nblocks; first += kThreads) {
+        const uint32_t i = first + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_counts[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, &total);
+        const uint32_t carry = carry_s;
+        if (i < nblocks) block_counts[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t runs = carry_s;
+        // DataChunk.cs:181-204: the first serializer (Raw) is kept unless RLE is strictly shorter
+        const bool rle = (unsigned long long)runs * 5ull < (unsigned long long)n;
+        meta->runs = runs;
+        meta->codec = rle ? 1u : 0u;
+        meta->out_len = 1ull + (rle ? (unsigned long long)runs * 5ull : (unsigned long long)n);
+        out[0] = rle ? 0x01 : 0x00;        // Serializer.SerializeCode, DataChunkSerializer.cs:20-23
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) scatter_runs(const uint8_t *__restrict__ p, size_t n, const uint32_t *__restrict__ block_offsets,
+                                                        const Meta *__restrict__ meta, uint32_t *__restrict__ starts, uint8_t *__restrict__ out)
+{
+    alignas(16) uint8_t bytes[kBytesPerThread];
+    const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
+    if (meta->codec == 0) {
+        // RawSerializer (DataChunkSerializer.cs:34-37): out[1 + i] = p[i].  The destination is
+        // 1 byte off alignment, so build aligned 32-bit words from two neighbouring source words.
+        if (base >= n) return;
+        const bool fast = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+        if (fast) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+            const uint32_t before = base ? (uint32_t)p[base - 1] : (uint32_t)out[0];   // header byte for the very first word
+            uint4 w;
+            w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
+            w.y = __byte_perm(v.x, v.y, 0x6543);          // {v.x.b3, v.y.b0, v.y.b1, v.y.b2}
+            w.z = __byte_perm(v.y, v.z, 0x6543);
+            w.w = __byte_perm(v.z, v.w, 0x6543);
+            *reinterpret_cast<uint4 *>(out + base) = w;   // covers out[base .. base+15] = {p[base-1], p[base .. base+14]}
+            if (base + kBytesPerThread == n) out[n] = (uint8_t)(v.w >> 24);           // last payload byte
+        } else {
+            // a word-building neighbour to the left leaves out[base] (= p[base-1]) to this thread
+            if (base) out[base] = p[base - 1];
+            for (int j = 0; j < kBytesPerThread && base + j < n; ++j) out[1 + base + j] = p[base + j];
+        }
+        return;
+    }
+    const uint32_t mask = start_mask(p, base, n, bytes);
+    uint32_t total;
+    uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(__popc(mask), &total);
+#pragma unroll
+    for (int j = 0; j < kBytesPerThread; ++j) {
+        if (mask & (1u << j)) {
+            starts[r] = (uint32_t)(base + j);
+            out[1 + (size_t)r * 5 + 4] = bytes[j];        // runValue (DataChunkSerializer.cs:84,98)
+            ++r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) write_run_lengths(const uint32_t *__restrict__ starts, size_t n, const Meta *__restrict__ meta,
+                                                             uint8_t *__restrict__ out)
+{
+    if (meta->codec == 0) return;
+    const uint32_t runs = meta->runs;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t len = (r + 1 < runs ? starts[r + 1] : (uint32_t)n) - starts[r];
+        uint8_t *rec = out + 1 + r * 5;                   // BitConverter.GetBytes(runLength): little-endian
+        rec[0] = (uint8_t)len;
+        rec[1] = (uint8_t)(len >> 8);
+        rec[2] = (uint8_t)(len >> 16);
+        rec[3] = (uint8_t)(len >> 24);
+    }
+}
+
+}  // namespace mbc

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "chunk_codec.cuh"
 #include "escape_kernels.cuh"
 
 namespace {
@@ -403,6 +404,111 @@ int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real
     if ((rc = mb_render_counts(&t, 1, static_cast<int32_t *>(c->scratch), dtype, c->stream))) return rc;
     MB_CUDA(cudaMemcpyAsync(host_out, c->scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+
+// ---- serialisation (f2) --------------------------------------------------------------------
+
+static size_t codec_blocks(size_t n) { return (n + mbc::kSegment - 1) / mbc::kSegment; }
+
+size_t mb_serialize_workspace_bytes(size_t n)
+{
+    // Meta | block counts/offsets | run starts (RLE is only kept when 5 * runs < n)
+    return 256 + sizeof(uint32_t) * (codec_blocks(n) + 1) + sizeof(uint32_t) * (n / 5 + 2) + 256;
+}
+
+int mb_serialize_chunk(const uint8_t *payload_dev, size_t n, uint8_t *out_dev, size_t out_capacity, void *workspace_dev,
+                       size_t workspace_bytes, uint64_t *out_len_dev, void *stream)
+{
+    if (!payload_dev || !out_dev || !workspace_dev) return fail(MB_ERR_INVALID, "NULL buffer");
+    if (n == 0 || n >= 0xffffffffull) return fail(MB_ERR_INVALID, "payload size must be in [1, 2^32)");
+    if (out_capacity < n + 1) return fail(MB_ERR_INVALID, "out_capacity must be >= n + 1");
+    if (workspace_bytes < mb_serialize_workspace_bytes(n)) return fail(MB_ERR_INVALID, "workspace too small");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nblocks = codec_blocks(n);
+    uint8_t *ws = static_cast<uint8_t *>(workspace_dev);
+    mbc::Meta *meta = reinterpret_cast<mbc::Meta *>(ws);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(ws + 256);
+    uint32_t *starts = counts + ((nblocks + 1 + 63) / 64) * 64;
+    mbc::count_run_starts<<<(unsigned)nblocks, mbc::kThreads, 0, st>>>(payload_dev, n, counts);
+    mbc::scan_block_counts<<<1, mbc::kThreads, 0, st>>>(counts, (uint32_t)nblocks, n, meta, out_dev);
+    mbc::scatter_runs<<<(unsigned)nblocks, mbc::kThreads, 0, st>>>(payload_dev, n, counts, meta, starts, out_dev);
+    mbc::write_run_lengths<<<grid_for(n / 5 + 1, c->sm_count), mbc::kThreads, 0, st>>>(starts, n, meta, out_dev);
+    MB_CUDA(cudaGetLastError());
+    if (out_len_dev)
+        MB_CUDA(cudaMemcpyAsync(out_len_dev, &meta->out_len, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return MB_OK;
+}
+
+// scratch layout of the host-pointer forms: payload[n] | out[n+1] (16B aligned) | workspace
+static int serialize_scratch(DeviceCtx *c, size_t n, uint8_t **payload, uint8_t **out, uint8_t **ws, size_t *ws_bytes)
+{
+    const size_t a = (n + 255) / 256 * 256, b = (n + 1 + 255) / 256 * 256;
+    *ws_bytes = mb_serialize_workspace_bytes(n);
+    int rc = ensure_scratch(c, a + b + *ws_bytes + 256);
+    if (rc) return rc;
+    *payload = static_cast<uint8_t *>(c->scratch);
+    *out = *payload + a;
+    *ws = *out + b;
+    return MB_OK;
+}
+
+int mb_serialize_chunk_host(const uint8_t *payload_host, size_t n, uint8_t *out_host, size_t out_capacity, uint64_t *out_len)
+{
+    if (!payload_host || !out_host || !out_len) return fail(MB_ERR_INVALID, "NULL buffer");
+    if (n == 0 || n >= 0xffffffffull) return fail(MB_ERR_INVALID, "payload size must be in [1, 2^32)");
+    if (out_capacity < n + 1) return fail(MB_ERR_INVALID, "out_capacity must be >= n + 1");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    uint8_t *p, *o, *ws;
+    size_t wsb;
+    if ((rc = serialize_scratch(c, n, &p, &o, &ws, &wsb))) return rc;
+    MB_CUDA(cudaMemcpyAsync(p, payload_host, n, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = mb_serialize_chunk(p, n, o, n + 1, ws, wsb, nullptr, c->stream))) return rc;
+    mbc::Meta meta;
+    MB_CUDA(cudaMemcpyAsync(&meta, ws, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    MB_CUDA(cudaMemcpyAsync(out_host, o, meta.out_len, cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    *out_len = meta.out_len;
+    return MB_OK;
+}
+
+int mb_process_workload_serialized(uint32_t level, uint32_t mrd, uint32_t index_real, uint32_t index_imag,
+                                   uint32_t definition, uint8_t *out_host, size_t out_capacity, uint64_t *out_len,
+                                   int32_t *entry_type)
+{
+    if (!out_host || !out_len || !entry_type) return fail(MB_ERR_INVALID, "NULL buffer");
+    mb_tile t;
+    int rc = mb_chunk_geometry(level, index_real, index_imag, definition, mrd, &t);
+    if (rc) return rc;
+    const size_t n = (size_t)definition * definition;
+    if (out_capacity < n + 1) return fail(MB_ERR_INVALID, "out_capacity must be >= definition^2 + 1");
+    DeviceCtx *c = nullptr;
+    if ((rc = current_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    uint8_t *p, *o, *ws;
+    size_t wsb;
+    if ((rc = serialize_scratch(c, n, &p, &o, &ws, &wsb))) return rc;
+    uint32_t *flags = reinterpret_cast<uint32_t *>(ws + wsb - 64);      // tail of the workspace pad
+    if ((rc = mb_render_u8(&t, 1, p, MB_DTYPE_F64, c->stream))) return rc;
+    if ((rc = mb_classify_u8(p, n, flags, c->stream))) return rc;
+    if ((rc = mb_serialize_chunk(p, n, o, n + 1, ws, wsb, nullptr, c->stream))) return rc;
+    mbc::Meta meta;
+    uint32_t hflags[2];
+    MB_CUDA(cudaMemcpyAsync(&meta, ws, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    MB_CUDA(cudaMemcpyAsync(out_host, o, meta.out_len, cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    *out_len = meta.out_len;
+    // IndexEntry.CreateIndexEntryForDataChunk (DataStorage.cs:71-84): Never is tested first
+    *entry_type = hflags[0] ? 1 : (hflags[1] ? 2 : 0);
     return MB_OK;
 }
 

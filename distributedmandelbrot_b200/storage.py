@@ -1,0 +1,133 @@
+"""In-box writer of the reference's on-disk format.
+
+When the GPUs of one box render a whole level themselves there is no reason to push every
+16 MiB payload through the Distributer's single-threaded TCP accept loop
+(Distributer.cs:226-297, 397-458) only for the server to classify it (DataChunk.cs:82,87),
+serialise it twice on one thread (DataChunk.cs:173-206) and append an index record
+(DataStorage.cs:410-427).  This module writes the SAME files the server would have written --
+`<parent>/Data/_index.dat` plus one file per Regular chunk -- so the unmodified DataServer/Viewer
+can serve a level rendered entirely in-box, and a restarted Distributer sees those chunks as
+completed (Distributer.cs:165-175).
+
+Classification and serialisation happen on the device (mb_process_workload_serialized); only
+the serialised bytes cross PCIe.  No CPU compute path exists here: without the CUDA library the
+render call raises.
+
+Formats:
+  index record  u32 level, u32 indexReal, u32 indexImag, i32 type (0 Regular, 1 Never,
+                2 Immediate) [, i32 filenameLength, ASCII filename]      DataStorage.cs:358-387
+  chunk file    name "{level};{ir};{ii}" + decimal suffix if taken       DataStorage.cs:392-405
+                content = 1 codec byte + raw payload or RLE records      DataChunkSerializer.cs
+"""
+from __future__ import annotations
+
+import ctypes as C
+import fcntl
+import os
+import struct
+
+import numpy as np
+
+from . import _native as nat
+
+DATA_DIRECTORY_NAME = "Data"          # DataStorage.dataDirectoryName (DataStorage.cs:15)
+INDEX_FILENAME = "_index.dat"         # DataStorage.indexFilename (DataStorage.cs:18)
+ENTRY_REGULAR, ENTRY_NEVER, ENTRY_IMMEDIATE = 0, 1, 2   # IndexEntry.Type (DataStorage.cs:41-49)
+
+
+class DataStore:
+    """`<parent>/Data/` in the reference's layout; append-only like DataStorage.SaveDataChunk."""
+
+    def __init__(self, parent: str):
+        self.dir = os.path.join(parent, DATA_DIRECTORY_NAME)
+        self.index_path = os.path.join(self.dir, INDEX_FILENAME)
+        # SetUpDataDirectoryIfNeeded (DataStorage.cs:131-141)
+        os.makedirs(self.dir, exist_ok=True)
+        if not os.path.exists(self.index_path):
+            open(self.index_path, "ab").close()
+
+    def generate_filename(self, level: int, ir: int, ii: int) -> str:
+        """GenerateDataChunkFilename (DataStorage.cs:392-405)."""
+        base = f"{level};{ir};{ii}"
+        if not os.path.exists(os.path.join(self.dir, base)):
+            return base
+        suffix = 0
+        while os.path.exists(os.path.join(self.dir, base + str(suffix))):
+            suffix += 1
+        return base + str(suffix)
+
+    def save(self, level: int, ir: int, ii: int, entry_type: int, serialized: bytes | memoryview | None) -> str | None:
+        """SaveDataChunk (DataStorage.cs:410-427): append the index record, then write the chunk
+        file for Regular entries.  The index append is serialised across PROCESSES with flock
+        (the reference only needs an in-process lock, DataStorage.cs:415)."""
+        filename = None
+        with open(self.index_path, "ab") as idx:
+            fcntl.flock(idx, fcntl.LOCK_EX)
+            try:
+                rec = struct.pack("<IIIi", level, ir, ii, entry_type)
+                if entry_type == ENTRY_REGULAR:
+                    filename = self.generate_filename(level, ir, ii)
+                    name = filename.encode("ascii")
+                    rec += struct.pack("<i", len(name)) + name
+                    # reserve the name while we still hold the lock (another rank may pick the next suffix)
+                    open(os.path.join(self.dir, filename), "ab").close()
+                idx.write(rec)
+                idx.flush()
+            finally:
+                fcntl.flock(idx, fcntl.LOCK_UN)
+        if filename is not None:
+            with open(os.path.join(self.dir, filename), "wb") as f:      # WriteDataToFile (DataStorage.cs:333-350)
+                f.write(serialized)
+        return filename
+
+    def completed(self):
+        """(level, ir, ii, type, filename) for every index record (ReadIndexEntry, DataStorage.cs:187-225)."""
+        buf = open(self.index_path, "rb").read()
+        pos, out = 0, []
+        while pos + 16 <= len(buf):
+            level, ir, ii, etype = struct.unpack_from("<IIIi", buf, pos)
+            pos += 16
+            name = None
+            if etype == ENTRY_REGULAR:
+                (ln,) = struct.unpack_from("<i", buf, pos)
+                pos += 4
+                name = buf[pos:pos + ln].decode("ascii")
+                pos += ln
+            out.append((level, ir, ii, etype, name))
+        return out
+
+
+def render_serialized(level: int, mrd: int, index_real: int, index_imag: int, *, definition: int = nat.CHUNK_DEFINITION,
+                      out: np.ndarray | None = None):
+    """process_workload + classify + serialise on the device -> (entry_type, memoryview of the
+    serialised chunk).  The view aliases `out` (definition^2 + 1 bytes, allocated if omitted)."""
+    nat.ensure_init()
+    n = int(definition) * int(definition)
+    if out is None:
+        out = np.empty(n + 1, dtype=np.uint8)
+    elif out.dtype != np.uint8 or out.size < n + 1 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 array of at least definition^2 + 1 bytes")
+    ln, et = C.c_uint64(), C.c_int32()
+    nat.check(nat.lib().mb_process_workload_serialized(level, mrd, index_real, index_imag, definition,
+                                                       out.ctypes.data_as(C.c_void_p), out.size, C.byref(ln), C.byref(et)))
+    return int(et.value), memoryview(out)[:ln.value]
+
+
+def render_level_to_store(store: DataStore, level: int, mrd: int, chunks=None, *, definition: int = nat.CHUNK_DEFINITION,
+                          skip_completed: bool = True) -> int:
+    """Render chunks of `level` (all level^2 of them unless `chunks` is given, e.g. an iterator
+    that pops indices from the in-box work-stealing queue) straight into the store.  Chunks the
+    index already holds are skipped, like the Distributer's resume (Distributer.cs:165-175)."""
+    have = {(l, r, i) for (l, r, i, _t, _f) in store.completed()} if skip_completed else set()
+    if chunks is None:
+        # Distributer.TryGetNextNeededWorkload order (Distributer.cs:335-353): indexReal outer, indexImag inner
+        chunks = ((ir, ii) for ir in range(level) for ii in range(level))
+    buf = np.empty(int(definition) * int(definition) + 1, dtype=np.uint8)
+    done = 0
+    for (ir, ii) in chunks:
+        if (level, ir, ii) in have:
+            continue
+        etype, blob = render_serialized(level, mrd, ir, ii, definition=definition, out=buf)
+        store.save(level, ir, ii, etype, blob if etype == ENTRY_REGULAR else None)
+        done += 1
+    return done

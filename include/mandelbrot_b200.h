@@ -150,6 +150,35 @@ int mb_useful_iterations(const int32_t *counts_dev, size_t n, uint32_t mrd, uint
  */
 int mb_classify_u8(const uint8_t *payload_dev, size_t n, uint32_t *flags_dev, void *stream);
 
+/* ---- DataChunk serialisation on the device ---------------------------------- */
+/*
+ * Replaces DataChunk.Serialize (DataChunk.cs:173-206) with its two serializers
+ * (DataChunkSerializer.cs:29-49 raw, :51-100 RLE): out = 1 codec byte (0x00 raw / 0x01 RLE) +
+ * either the n payload bytes or one (uint32 LE runLength, uint8 value) record per maximal run;
+ * RLE only when strictly shorter.  out_dev needs n + 1 bytes; *out_len_dev (device uint64)
+ * receives the serialised length.  workspace_dev: mb_serialize_workspace_bytes(n) bytes.
+ * n < 2^32.  Asynchronous on `stream`.
+ */
+size_t mb_serialize_workspace_bytes(size_t n);
+int mb_serialize_chunk(const uint8_t *payload_dev, size_t n, uint8_t *out_dev, size_t out_capacity,
+                       void *workspace_dev, size_t workspace_bytes, uint64_t *out_len_dev,
+                       void *stream);
+/* host-pointer form (copies in, serialises on the device, copies the result out; synchronous) */
+int mb_serialize_chunk_host(const uint8_t *payload_host, size_t n, uint8_t *out_host,
+                            size_t out_capacity, uint64_t *out_len);
+
+/*
+ * process_workload + what the server does with the result on arrival, in one call and without
+ * the 16 MiB round trip: render (.py:70-100), classify (DataChunk.cs:82,87 ->
+ * IndexEntry type, DataStorage.cs:71-84: 0 Regular, 1 Never, 2 Immediate) and serialise
+ * (DataChunk.cs:173-206) on the device; only the serialised bytes come back.
+ * out_host: definition^2 + 1 bytes.  For Never/Immediate chunks the reference stores no file
+ * (DataStorage.cs:424-425): *out_len is still set, callers may ignore the bytes.
+ */
+int mb_process_workload_serialized(uint32_t level, uint32_t mrd, uint32_t index_real,
+                                   uint32_t index_imag, uint32_t definition, uint8_t *out_host,
+                                   size_t out_capacity, uint64_t *out_len, int32_t *entry_type);
+
 /* ---- one-call equivalents of process_workload (host buffers, synchronous) ------------- */
 
 /*

@@ -189,6 +189,32 @@ def main() -> None:
         meta["f32"].append({"level": level, "mrd": mrd, "ir": ir, "ii": ii, "d": d, "key": key,
                             "useful": useful(c, mrd), "pinned": "unpinned upstream (numpy restatement)"})
 
+    # DataChunk serialisation (f2): the restated serializer (oracle/chunk_codec.py, following
+    # DataChunkSerializer.cs) is pinned against the reference VIEWER's own decoder text
+    # (DistributedMandelbrotViewer.py:35-60, pure Python), executed here.
+    import chunk_codec
+    vsrc = open("/root/reference/DistributedMandelbrotViewer/DistributedMandelbrotViewer.py", encoding="utf-8-sig").read().splitlines()
+    vns = {"unpack": __import__("struct").unpack}
+    exec(compile("\n".join(vsrc[34:60]) + "\n", "Viewer.py:35-60", "exec"), vns)
+    rng = np.random.default_rng(2024)
+    payloads = {
+        "codec_all7_n4096": np.full(4096, 7, np.uint8),
+        "codec_alternating_n1000": (np.arange(1000) % 2).astype(np.uint8),
+        "codec_single_n1": np.array([200], np.uint8),
+        "codec_runs_n10007": np.repeat(rng.integers(0, 256, 700).astype(np.uint8), rng.integers(1, 30, 700))[:10007],
+        "codec_tie_n20": np.repeat(np.array([1, 2, 3, 4], np.uint8), 5),           # 4 runs * 5 B == 20 B: Raw wins the tie
+        "codec_chunk_L10_m1024_r3_i5_d128": arrays["L10_m1024_r3_i5_d128_u8"].ravel(),
+        "codec_chunk_L4_m256_r0_i0_d32": arrays["L4_m256_r0_i0_d32_u8"].ravel(),
+    }
+    meta["codec"] = []
+    for key, payload in payloads.items():
+        blob = chunk_codec.serialize(payload)
+        decoded = bytes(vns["chunk_data_to_value_array"](bytearray(blob)))
+        assert decoded == payload.tobytes(), key            # the reference's own decoder accepts it
+        arrays[key + "_payload"] = payload
+        arrays[key + "_serialized"] = np.frombuffer(blob, dtype=np.uint8)
+        meta["codec"].append({"key": key, "n": int(payload.size), "codec": int(blob[0]), "serialized_len": len(blob)})
+
     np.savez_compressed(os.path.join(OUT, "golden_arrays.npz"), **arrays)
     with open(os.path.join(OUT, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)

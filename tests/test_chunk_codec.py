@@ -1,0 +1,136 @@
+"""DataChunk serialisation and the in-box storage writer (f3).
+
+CPU: the restated serializer against fixtures whose bytes the reference viewer's own decoder
+accepted (oracle/gen_golden.py), and the storage record format.  GPU (-m gpu): the device
+serializer / classifier / storage writer against that restatement, byte for byte."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import chunk_codec
+    return chunk_codec
+
+
+def test_restated_serializer_matches_golden(codec, golden_meta, golden_arrays):
+    for rec in golden_meta["codec"]:
+        payload = golden_arrays[rec["key"] + "_payload"]
+        blob = codec.serialize(payload)
+        assert blob == golden_arrays[rec["key"] + "_serialized"].tobytes(), rec
+        assert blob[0] == rec["codec"] and len(blob) == rec["serialized_len"]
+        assert np.array_equal(codec.deserialize(blob, payload.size), payload)
+
+
+def test_known_encodings(codec):
+    # an all-7 chunk RLE-encodes as 01 | 00 00 00 01 | 07
+    assert codec.serialize(np.full(16_777_216, 7, np.uint8)) == bytes.fromhex("01" "00000001" "07")
+    assert codec.serialize(np.array([5, 5, 5, 9], np.uint8)) == bytes([0, 5, 5, 5, 9])        # 2 runs * 5 > 4: raw
+    assert codec.serialize(np.array([5] * 11 + [9] * 2, np.uint8)) == b"\x01" + struct.pack("<IB", 11, 5) + struct.pack("<IB", 2, 9)
+    assert codec.serialize(np.repeat(np.array([1, 2, 3, 4], np.uint8), 5))[0] == 0            # tie -> Raw (DataChunk.cs:188)
+    with pytest.raises(ValueError):
+        codec.deserialize(b"\x02abc", 3)
+    with pytest.raises(ValueError):
+        codec.deserialize(b"\x01" + struct.pack("<IB", 0, 1), 3)
+
+
+def test_storage_layout_and_records(tmp_path, codec):
+    from distributedmandelbrot_b200.storage import DataStore, ENTRY_IMMEDIATE, ENTRY_NEVER, ENTRY_REGULAR
+    st = DataStore(str(tmp_path))
+    assert os.path.isdir(tmp_path / "Data") and os.path.getsize(tmp_path / "Data" / "_index.dat") == 0
+    blob = codec.serialize(np.arange(64, dtype=np.uint8))
+    assert st.save(4, 1, 2, ENTRY_REGULAR, blob) == "4;1;2"
+    assert st.save(4, 0, 0, ENTRY_IMMEDIATE, None) is None
+    assert st.save(4, 1, 1, ENTRY_NEVER, None) is None
+    assert st.save(4, 1, 2, ENTRY_REGULAR, blob) == "4;1;20"       # GenerateDataChunkFilename suffix (DataStorage.cs:400-403)
+    assert st.save(4, 1, 2, ENTRY_REGULAR, blob) == "4;1;21"
+    raw = open(tmp_path / "Data" / "_index.dat", "rb").read()
+    want = (codec.index_entry(4, 1, 2, 0, "4;1;2") + codec.index_entry(4, 0, 0, 2) + codec.index_entry(4, 1, 1, 1) +
+            codec.index_entry(4, 1, 2, 0, "4;1;20") + codec.index_entry(4, 1, 2, 0, "4;1;21"))
+    assert raw == want
+    assert raw[:25] == bytes.fromhex("04000000" "01000000" "02000000" "00000000" "05000000") + b"4;1;2"
+    assert codec.parse_index(raw) == st.completed()
+    assert open(tmp_path / "Data" / "4;1;2", "rb").read() == blob
+    # a second store on the same directory appends, it does not truncate (resume, Distributer.cs:165-175)
+    st2 = DataStore(str(tmp_path))
+    assert len(st2.completed()) == 5
+
+
+# ---- GPU -----------------------------------------------------------------------------------------
+
+def _serialize_gpu(native, payload):
+    out = np.full(payload.size + 1 + 7, 0xEE, np.uint8)
+    ln = C.c_uint64()
+    native.check(native.lib().mb_serialize_chunk_host(payload.ctypes.data_as(C.c_void_p), payload.size,
+                                                       out.ctypes.data_as(C.c_void_p), payload.size + 1, C.byref(ln)))
+    assert (out[payload.size + 1:] == 0xEE).all(), "wrote past n + 1 bytes"
+    return out[:ln.value].tobytes()
+
+
+@pytest.mark.gpu
+def test_device_serializer_golden_and_shapes(gpu, codec, golden_meta, golden_arrays):
+    for rec in golden_meta["codec"]:
+        payload = np.ascontiguousarray(golden_arrays[rec["key"] + "_payload"])
+        assert _serialize_gpu(gpu, payload) == golden_arrays[rec["key"] + "_serialized"].tobytes(), rec
+    rng = np.random.default_rng(3)
+    for n in [1, 2, 15, 16, 17, 31, 4095, 4096, 4097, 8192, 100_003, 1_000_000]:
+        for kind in ("runs", "noise", "const", "alt"):
+            if kind == "runs":
+                p = np.repeat(rng.integers(0, 4, n // 3 + 2).astype(np.uint8), rng.integers(1, 12, n // 3 + 2))[:n]
+            elif kind == "noise":
+                p = rng.integers(0, 256, n).astype(np.uint8)
+            elif kind == "const":
+                p = np.full(n, 1, np.uint8)
+            else:
+                p = (np.arange(n) % 2).astype(np.uint8)
+            p = np.ascontiguousarray(p)
+            assert p.size == n
+            assert _serialize_gpu(gpu, p) == codec.serialize(p), (n, kind)
+
+
+@pytest.mark.gpu
+def test_device_serializer_exactly_at_the_raw_rle_threshold(gpu, codec):
+    # 5 * runs < n picks RLE, 5 * runs == n keeps Raw (DataChunk.cs:188)
+    for runs, n in [(20, 100), (19, 100), (21, 100), (819, 4096), (820, 4096)]:
+        lens = np.full(runs, n // runs)
+        lens[: n - lens.sum()] += 1
+        p = np.ascontiguousarray(np.repeat((np.arange(runs) % 251).astype(np.uint8), lens))
+        assert p.size == n
+        blob = _serialize_gpu(gpu, p)
+        assert blob == codec.serialize(p)
+        assert blob[0] == (1 if 5 * runs < n else 0)
+
+
+@pytest.mark.gpu
+def test_native_chunk_serialized_and_classified(gpu, codec, oracle):
+    """Full 4096^2 DataChunks through render + classify + serialise on the device."""
+    from distributedmandelbrot_b200.storage import render_serialized
+    for (level, mrd, ir, ii, want_type) in [(4, 256, 1, 2, 0), (8, 64, 3, 4, 1), (4, 2, 0, 0, 2)]:
+        etype, blob = render_serialized(level, mrd, ir, ii)
+        payload = oracle.process_workload(level, mrd, ir, ii, 4096)
+        assert etype == want_type == codec.entry_type(payload)
+        assert bytes(blob) == codec.serialize(payload)
+        assert np.array_equal(codec.deserialize(bytes(blob), 4096 * 4096), payload)      # round trip at full size
+
+
+@pytest.mark.gpu
+def test_render_level_to_store(gpu, codec, oracle, tmp_path):
+    from distributedmandelbrot_b200.storage import DataStore, render_level_to_store
+    st = DataStore(str(tmp_path))
+    level, mrd, d = 4, 40, 96
+    assert render_level_to_store(st, level, mrd, definition=d) == 16
+    entries = st.completed()
+    assert [(e[1], e[2]) for e in entries] == [(ir, ii) for ir in range(4) for ii in range(4)]   # Distributer order
+    for (lv, ir, ii, etype, name) in entries:
+        payload = oracle.process_workload(lv, mrd, ir, ii, d)
+        assert etype == codec.entry_type(payload)
+        if etype == 0:
+            blob = open(os.path.join(st.dir, name), "rb").read()
+            assert blob == codec.serialize(payload)
+        else:
+            assert name is None
+    assert render_level_to_store(st, level, mrd, definition=d) == 0                                # resume: nothing left
