@@ -109,7 +109,7 @@ def test_device_serializer_exactly_at_the_raw_rle_threshold(gpu, codec):
 def test_native_chunk_serialized_and_classified(gpu, codec, oracle):
     """Full 4096^2 DataChunks through render + classify + serialise on the device."""
     from distributedmandelbrot_b200.storage import render_serialized
-    for (level, mrd, ir, ii, want_type) in [(4, 256, 1, 2, 0), (8, 64, 3, 4, 1), (4, 2, 0, 0, 2)]:
+    for (level, mrd, ir, ii, want_type) in [(4, 256, 1, 2, 0), (8, 64, 3, 4, 1), (8, 300, 0, 0, 2)]:
         etype, blob = render_serialized(level, mrd, ir, ii)
         payload = oracle.process_workload(level, mrd, ir, ii, 4096)
         assert etype == want_type == codec.entry_type(payload)
