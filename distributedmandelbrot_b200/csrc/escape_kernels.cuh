@@ -137,34 +137,38 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
             } else if (n >= HEAD && !risky) {
                 // steady state: deferred blocks in a tight per-lane loop (no vote inside);
                 // K untested updates, one test, exact replay of the block on escape
-                // The hot loop only DETECTS an escape; the replay happens after it, from the saved
-                // start (sx, sy) of the block that tripped.  Two blocks per trip in explicit SSA
-                // form so that block starts stay live in registers without copies.
-                Real sx = x, sy = y;
+                // The hot loop only DETECTS an escape; the replay (cold) starts from (x, y), which
+                // every exit leaves at the start of the block that tripped.  Two blocks per trip in
+                // explicit SSA form: block A reads (x, y) without overwriting them, block B reads
+                // A's results, and only the cold exit of B copies A's start into (x, y).
                 bool tripped = false;
-                while (left >= 2 * K) {
-                    Real ax = x, ay = y, axx = xx, ayy = yy;
+                {
+                    Real ax, ay, axx, ayy, bx, by, bxx, byy;
+                    while (left >= 2 * K) {
+                        ax = x; ay = y; axx = xx; ayy = yy;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
-                    if (Defer<Real>::tripped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; break; }
-                    Real bx = ax, by = ay, bxx = axx, byy = ayy;
+                        for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
+                        if (Defer<Real>::tripped(O::add(axx, ayy))) { tripped = true; break; }
+                        bx = ax; by = ay; bxx = axx; byy = ayy;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) update<Real>(bx, by, bxx, byy, cr, ci);
-                    if (Defer<Real>::tripped(O::add(bxx, byy))) { sx = ax; sy = ay; n += K; left -= K; tripped = true; break; }
-                    x = bx; y = by; xx = bxx; yy = byy;
-                    n += 2 * K;
-                    left -= 2 * K;
-                }
-                if (!tripped && left >= K) {
-                    Real ax = x, ay = y, axx = xx, ayy = yy;
+                        for (int j = 0; j < K; ++j) update<Real>(bx, by, bxx, byy, cr, ci);
+                        n += K;
+                        left -= K;
+                        if (Defer<Real>::tripped(O::add(bxx, byy))) { x = ax; y = ay; tripped = true; break; }
+                        x = bx; y = by; xx = bxx; yy = byy;
+                        n += K;
+                        left -= K;
+                    }
+                    if (!tripped && left >= K) {
+                        ax = x; ay = y; axx = xx; ayy = yy;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
-                    if (Defer<Real>::tripped(O::add(axx, ayy))) { sx = x; sy = y; tripped = true; }
-                    else { x = ax; y = ay; xx = axx; yy = ayy; n += K; left -= K; }
+                        for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
+                        if (Defer<Real>::tripped(O::add(axx, ayy))) tripped = true;
+                        else { x = ax; y = ay; xx = axx; yy = ayy; n += K; left -= K; }
+                    }
                 }
                 if (tripped) {
                     // exact replay of the block that escaped: test after every update (.py:62-66)
-                    x = sx; y = sy;
                     xx = O::mul(x, x); yy = O::mul(y, y);
                     for (int j = 1; j <= K; ++j) {
                         update<Real>(x, y, xx, yy, cr, ci);
