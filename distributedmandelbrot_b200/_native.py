@@ -58,6 +58,15 @@ class Tile(C.Structure):
 
 assert C.sizeof(Tile) == 88
 
+
+class ChunkInfo(C.Structure):
+    """mb_chunk_info: result record of the device serializer for one chunk."""
+    _fields_ = [("out_len", C.c_uint64), ("runs", C.c_uint32), ("codec", C.c_uint32),
+                ("entry_type", C.c_uint32), ("first_value", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+
+
+assert C.sizeof(ChunkInfo) == 32
+
 _lib = None
 _lock = threading.Lock()
 
@@ -80,8 +89,9 @@ SIGNATURES = {
     "mb_counts_to_u8": (_int, [_vp, _vp, _sz, _u32, _vp]),
     "mb_useful_iterations": (_int, [_vp, _sz, _u32, _vp, _vp]),
     "mb_classify_u8": (_int, [_vp, _sz, _vp, _vp]),
-    "mb_serialize_workspace_bytes": (_sz, [_sz]),
-    "mb_serialize_chunk": (_int, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "mb_serialize_out_stride": (_sz, [_sz]),
+    "mb_serialize_workspace_bytes": (_sz, [_sz, _u32]),
+    "mb_serialize_chunks": (_int, [_vp, _sz, _u32, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "mb_serialize_chunk_host": (_int, [_vp, _sz, _vp, _sz, C.POINTER(_u64)]),
     "mb_process_workload_serialized": (_int, [_u32, _u32, _u32, _u32, _u32, _vp, _sz, C.POINTER(_u64), C.POINTER(_i32)]),
     "mb_process_workload_u8": (_int, [_u32, _u32, _u32, _u32, _u32, _vp]),

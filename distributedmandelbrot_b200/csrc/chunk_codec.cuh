@@ -24,10 +24,30 @@ constexpr int kThreads = 256;
 constexpr int kBytesPerThread = 16;
 constexpr int kSegment = kThreads * kBytesPerThread;   // 4096 payload bytes per CTA
 
+// per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
     unsigned long long out_len;   // total serialised bytes, header included
     uint32_t runs;
     uint32_t codec;               // 0 raw, 1 RLE
+    uint32_t entry_type;          // IndexEntry.Type (DataStorage.cs:41-49): 0 Regular, 1 Never, 2 Immediate
+    uint32_t first_value;
+    uint32_t pad[2];
+};
+static_assert(sizeof(Meta) == 32, "mb_chunk_info layout");
+
+// A batch of chunks is processed by one set of launches: blockIdx.y = chunk.
+struct Batch {
+    const uint8_t *payloads;      // chunk c at payloads + c * payload_stride
+    size_t payload_stride;
+    uint8_t *out;                 // chunk c at out + c * out_stride (16-byte aligned stride)
+    size_t out_stride;
+    uint32_t *counts;             // per chunk: counts + c * counts_stride
+    size_t counts_stride;
+    uint32_t *starts;             // per chunk: starts + c * starts_stride
+    size_t starts_stride;
+    Meta *meta;                   // meta[c]
+    size_t n;                     // payload bytes per chunk
+    uint32_t nblocks;             // CTAs per chunk
 };
 
 // 16-bit mask: bit j set iff byte j of this thread's 16-byte span starts a run
@@ -76,8 +96,11 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kThreads) count_run_starts(const uint8_t *__restrict__ p, size_t n, uint32_t *__restrict__ block_counts)
+__global__ void __launch_bounds__(kThreads) count_run_starts(const Batch b)
 {
+    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
+    uint32_t *__restrict__ block_counts = b.counts + blockIdx.y * b.counts_stride;
+    const size_t n = b.n;
     alignas(16) uint8_t bytes[kBytesPerThread];
     const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
     const uint32_t c = __popc(start_mask(p, base, n, bytes));
@@ -86,10 +109,15 @@ __global__ void __launch_bounds__(kThreads) count_run_starts(const uint8_t *__re
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
-// one CTA; in-place exclusive scan of block_counts[0..nblocks)
-__global__ void __launch_bounds__(kThreads) scan_block_counts(uint32_t *__restrict__ block_counts, uint32_t nblocks, size_t n,
-                                                             Meta *__restrict__ meta, uint8_t *__restrict__ out)
+// one CTA per chunk; in-place exclusive scan of block_counts[0..nblocks)
+__global__ void __launch_bounds__(kThreads) scan_block_counts(const Batch b)
 {
+    uint32_t *__restrict__ block_counts = b.counts + blockIdx.x * b.counts_stride;
+    Meta *__restrict__ meta = b.meta + blockIdx.x;
+    uint8_t *__restrict__ out = b.out + blockIdx.x * b.out_stride;
+    const uint8_t *__restrict__ p = b.payloads + blockIdx.x * b.payload_stride;
+    const uint32_t nblocks = b.nblocks;
+    const size_t n = b.n;
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -111,13 +139,23 @@ __global__ void __launch_bounds__(kThreads) scan_block_counts(uint32_t *__restri
         meta->runs = runs;
         meta->codec = rle ? 1u : 0u;
         meta->out_len = 1ull + (rle ? (unsigned long long)runs * 5ull : (unsigned long long)n);
+        // one run of 0s = IsNeverChunk, one run of 1s = IsImmediateChunk (DataChunk.cs:82,87);
+        // Never is tested first (DataStorage.cs:74-77) but the two cannot both hold
+        const uint32_t v0 = p[0];
+        meta->first_value = v0;
+        meta->entry_type = (runs == 1 && v0 == 0) ? 1u : (runs == 1 && v0 == 1) ? 2u : 0u;
         out[0] = rle ? 0x01 : 0x00;        // Serializer.SerializeCode, DataChunkSerializer.cs:20-23
     }
 }
 
-__global__ void __launch_bounds__(kThreads) scatter_runs(const uint8_t *__restrict__ p, size_t n, const uint32_t *__restrict__ block_offsets,
-                                                        const Meta *__restrict__ meta, uint32_t *__restrict__ starts, uint8_t *__restrict__ out)
+__global__ void __launch_bounds__(kThreads) scatter_runs(const Batch b)
 {
+    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
+    const uint32_t *__restrict__ block_offsets = b.counts + blockIdx.y * b.counts_stride;
+    const Meta *__restrict__ meta = b.meta + blockIdx.y;
+    uint32_t *__restrict__ starts = b.starts + blockIdx.y * b.starts_stride;
+    uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
+    const size_t n = b.n;
     alignas(16) uint8_t bytes[kBytesPerThread];
     const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
     if (meta->codec == 0) {
@@ -156,9 +194,12 @@ __global__ void __launch_bounds__(kThreads) scatter_runs(const uint8_t *__restri
     }
 }
 
-__global__ void __launch_bounds__(kThreads) write_run_lengths(const uint32_t *__restrict__ starts, size_t n, const Meta *__restrict__ meta,
-                                                             uint8_t *__restrict__ out)
+__global__ void __launch_bounds__(kThreads) write_run_lengths(const Batch b)
 {
+    const Meta *__restrict__ meta = b.meta + blockIdx.y;
+    const uint32_t *__restrict__ starts = b.starts + blockIdx.y * b.starts_stride;
+    uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
+    const size_t n = b.n;
     if (meta->codec == 0) return;
     const uint32_t runs = meta->runs;
     for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (size_t)gridDim.x * blockDim.x) {

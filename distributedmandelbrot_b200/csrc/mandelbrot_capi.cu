@@ -410,47 +410,63 @@ int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real
 // ---- serialisation (f2) --------------------------------------------------------------------
 
 static size_t codec_blocks(size_t n) { return (n + mbc::kSegment - 1) / mbc::kSegment; }
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static size_t codec_counts_stride(size_t n) { return round_up(codec_blocks(n) + 1, 64); }
+static size_t codec_starts_stride(size_t n) { return round_up(n / 5 + 2, 64); }
 
-size_t mb_serialize_workspace_bytes(size_t n)
+size_t mb_serialize_out_stride(size_t n) { return round_up(n + 1, 256); }
+
+size_t mb_serialize_workspace_bytes(size_t n, uint32_t n_chunks)
 {
-    // Meta | block counts/offsets | run starts (RLE is only kept when 5 * runs < n)
-    return 256 + sizeof(uint32_t) * (codec_blocks(n) + 1) + sizeof(uint32_t) * (n / 5 + 2) + 256;
+    // per chunk: block counts/offsets | run starts (RLE is only kept when 5 * runs < n)
+    return 256 + (size_t)n_chunks * sizeof(uint32_t) * (codec_counts_stride(n) + codec_starts_stride(n));
 }
 
-int mb_serialize_chunk(const uint8_t *payload_dev, size_t n, uint8_t *out_dev, size_t out_capacity, void *workspace_dev,
-                       size_t workspace_bytes, uint64_t *out_len_dev, void *stream)
+int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks, size_t payload_stride, uint8_t *out_dev,
+                        size_t out_stride, void *workspace_dev, size_t workspace_bytes, mb_chunk_info *info_dev, void *stream)
 {
-    if (!payload_dev || !out_dev || !workspace_dev) return fail(MB_ERR_INVALID, "NULL buffer");
+    if (!payloads_dev || !out_dev || !workspace_dev || !info_dev) return fail(MB_ERR_INVALID, "NULL buffer");
     if (n == 0 || n >= 0xffffffffull) return fail(MB_ERR_INVALID, "payload size must be in [1, 2^32)");
-    if (out_capacity < n + 1) return fail(MB_ERR_INVALID, "out_capacity must be >= n + 1");
-    if (workspace_bytes < mb_serialize_workspace_bytes(n)) return fail(MB_ERR_INVALID, "workspace too small");
+    if (n_chunks == 0 || n_chunks > 65535) return fail(MB_ERR_INVALID, "n_chunks must be in [1, 65535]");
+    if (payload_stride < n) return fail(MB_ERR_INVALID, "payload_stride < n");
+    if (out_stride < n + 1) return fail(MB_ERR_INVALID, "out_stride must be >= n + 1");
+    if (workspace_bytes < mb_serialize_workspace_bytes(n, n_chunks)) return fail(MB_ERR_INVALID, "workspace too small");
+    static_assert(sizeof(mb_chunk_info) == sizeof(mbc::Meta), "mb_chunk_info mirrors mbc::Meta");
     DeviceCtx *c = nullptr;
     int rc = current_ctx(&c);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t nblocks = codec_blocks(n);
-    uint8_t *ws = static_cast<uint8_t *>(workspace_dev);
-    mbc::Meta *meta = reinterpret_cast<mbc::Meta *>(ws);
-    uint32_t *counts = reinterpret_cast<uint32_t *>(ws + 256);
-    uint32_t *starts = counts + ((nblocks + 1 + 63) / 64) * 64;
-    mbc::count_run_starts<<<(unsigned)nblocks, mbc::kThreads, 0, st>>>(payload_dev, n, counts);
-    mbc::scan_block_counts<<<1, mbc::kThreads, 0, st>>>(counts, (uint32_t)nblocks, n, meta, out_dev);
-    mbc::scatter_runs<<<(unsigned)nblocks, mbc::kThreads, 0, st>>>(payload_dev, n, counts, meta, starts, out_dev);
-    mbc::write_run_lengths<<<grid_for(n / 5 + 1, c->sm_count), mbc::kThreads, 0, st>>>(starts, n, meta, out_dev);
+    mbc::Batch b;
+    b.payloads = payloads_dev;
+    b.payload_stride = payload_stride;
+    b.out = out_dev;
+    b.out_stride = out_stride;
+    b.counts = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(workspace_dev) + 256);
+    b.counts_stride = codec_counts_stride(n);
+    b.starts = b.counts + (size_t)n_chunks * b.counts_stride;
+    b.starts_stride = codec_starts_stride(n);
+    b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
+    b.n = n;
+    b.nblocks = (uint32_t)codec_blocks(n);
+    const dim3 per_chunk(b.nblocks, n_chunks, 1);
+    mbc::count_run_starts<<<per_chunk, mbc::kThreads, 0, st>>>(b);
+    mbc::scan_block_counts<<<n_chunks, mbc::kThreads, 0, st>>>(b);
+    mbc::scatter_runs<<<per_chunk, mbc::kThreads, 0, st>>>(b);
+    const dim3 len_grid((unsigned)grid_for(n / 5 + 1, c->sm_count), n_chunks, 1);
+    mbc::write_run_lengths<<<len_grid, mbc::kThreads, 0, st>>>(b);
     MB_CUDA(cudaGetLastError());
-    if (out_len_dev)
-        MB_CUDA(cudaMemcpyAsync(out_len_dev, &meta->out_len, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     return MB_OK;
 }
 
-// scratch layout of the host-pointer forms: payload[n] | out[n+1] (16B aligned) | workspace
-static int serialize_scratch(DeviceCtx *c, size_t n, uint8_t **payload, uint8_t **out, uint8_t **ws, size_t *ws_bytes)
+// scratch layout of the host-pointer forms: info | payload[n] | out[n+1] (256B aligned) | workspace
+static int serialize_scratch(DeviceCtx *c, size_t n, mb_chunk_info **info, uint8_t **payload, uint8_t **out, uint8_t **ws, size_t *ws_bytes)
 {
-    const size_t a = (n + 255) / 256 * 256, b = (n + 1 + 255) / 256 * 256;
-    *ws_bytes = mb_serialize_workspace_bytes(n);
-    int rc = ensure_scratch(c, a + b + *ws_bytes + 256);
+    const size_t a = round_up(n, 256), b = mb_serialize_out_stride(n);
+    *ws_bytes = mb_serialize_workspace_bytes(n, 1);
+    int rc = ensure_scratch(c, 256 + a + b + *ws_bytes);
     if (rc) return rc;
-    *payload = static_cast<uint8_t *>(c->scratch);
+    *info = static_cast<mb_chunk_info *>(c->scratch);
+    *payload = static_cast<uint8_t *>(c->scratch) + 256;
     *out = *payload + a;
     *ws = *out + b;
     return MB_OK;
@@ -465,17 +481,18 @@ int mb_serialize_chunk_host(const uint8_t *payload_host, size_t n, uint8_t *out_
     int rc = current_ctx(&c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
+    mb_chunk_info *info;
     uint8_t *p, *o, *ws;
     size_t wsb;
-    if ((rc = serialize_scratch(c, n, &p, &o, &ws, &wsb))) return rc;
+    if ((rc = serialize_scratch(c, n, &info, &p, &o, &ws, &wsb))) return rc;
     MB_CUDA(cudaMemcpyAsync(p, payload_host, n, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = mb_serialize_chunk(p, n, o, n + 1, ws, wsb, nullptr, c->stream))) return rc;
-    mbc::Meta meta;
-    MB_CUDA(cudaMemcpyAsync(&meta, ws, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mb_serialize_chunks(p, n, 1, n, o, mb_serialize_out_stride(n), ws, wsb, info, c->stream))) return rc;
+    mb_chunk_info h;
+    MB_CUDA(cudaMemcpyAsync(&h, info, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
-    MB_CUDA(cudaMemcpyAsync(out_host, o, meta.out_len, cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaMemcpyAsync(out_host, o, h.out_len, cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
-    *out_len = meta.out_len;
+    *out_len = h.out_len;
     return MB_OK;
 }
 
@@ -492,23 +509,20 @@ int mb_process_workload_serialized(uint32_t level, uint32_t mrd, uint32_t index_
     DeviceCtx *c = nullptr;
     if ((rc = current_ctx(&c))) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
+    mb_chunk_info *info;
     uint8_t *p, *o, *ws;
     size_t wsb;
-    if ((rc = serialize_scratch(c, n, &p, &o, &ws, &wsb))) return rc;
-    uint32_t *flags = reinterpret_cast<uint32_t *>(ws + wsb - 64);      // tail of the workspace pad
+    if ((rc = serialize_scratch(c, n, &info, &p, &o, &ws, &wsb))) return rc;
     if ((rc = mb_render_u8(&t, 1, p, MB_DTYPE_F64, c->stream))) return rc;
-    if ((rc = mb_classify_u8(p, n, flags, c->stream))) return rc;
-    if ((rc = mb_serialize_chunk(p, n, o, n + 1, ws, wsb, nullptr, c->stream))) return rc;
-    mbc::Meta meta;
-    uint32_t hflags[2];
-    MB_CUDA(cudaMemcpyAsync(&meta, ws, sizeof(meta), cudaMemcpyDeviceToHost, c->stream));
-    MB_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mb_serialize_chunks(p, n, 1, n, o, mb_serialize_out_stride(n), ws, wsb, info, c->stream))) return rc;
+    mb_chunk_info h;
+    MB_CUDA(cudaMemcpyAsync(&h, info, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
-    MB_CUDA(cudaMemcpyAsync(out_host, o, meta.out_len, cudaMemcpyDeviceToHost, c->stream));
+    // Never/Immediate chunks have no file (DataStorage.cs:424-425) but the 6 bytes are cheap to return anyway
+    MB_CUDA(cudaMemcpyAsync(out_host, o, h.out_len, cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
-    *out_len = meta.out_len;
-    // IndexEntry.CreateIndexEntryForDataChunk (DataStorage.cs:71-84): Never is tested first
-    *entry_type = hflags[0] ? 1 : (hflags[1] ? 2 : 0);
+    *out_len = h.out_len;
+    *entry_type = (int32_t)h.entry_type;   // classification falls out of the run count (chunk_codec.cuh)
     return MB_OK;
 }
 

@@ -113,21 +113,60 @@ def render_serialized(level: int, mrd: int, index_real: int, index_imag: int, *,
     return int(et.value), memoryview(out)[:ln.value]
 
 
+INFO_DTYPE = np.dtype([("out_len", "<u8"), ("runs", "<u4"), ("codec", "<u4"), ("entry_type", "<u4"),
+                       ("first_value", "<u4"), ("reserved", "<u4", (2,))])     # mb_chunk_info
+assert INFO_DTYPE.itemsize == C.sizeof(nat.ChunkInfo)
+
+
+def render_serialized_batch(workloads, *, definition: int = nat.CHUNK_DEFINITION):
+    """Render + classify + serialise a batch of (level, mrd, ir, ii) in ONE set of launches
+    (one escape-kernel launch over all chunks, four serializer launches over all chunks).
+    Returns (infos: structured numpy array, fetch(k) -> bytes of chunk k's serialised form)."""
+    import torch
+    dev = torch.device("cuda", nat.ensure_init())
+    lib = nat.lib()
+    workloads = list(workloads)
+    nb = len(workloads)
+    n = int(definition) * int(definition)
+    stride = lib.mb_serialize_out_stride(n)
+    wsb = lib.mb_serialize_workspace_bytes(n, nb)
+    payload = torch.empty(nb * n, dtype=torch.uint8, device=dev)
+    out = torch.empty(nb * stride, dtype=torch.uint8, device=dev)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    info = torch.empty(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    tiles = []
+    for k, (level, mrd, ir, ii) in enumerate(workloads):
+        t = nat.chunk_geometry(level, ir, ii, definition, mrd)
+        t.out_offset = k * n
+        tiles.append(t)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    nat.check(lib.mb_render_u8(nat.tile_array(tiles), nb, payload.data_ptr(), nat.DTYPE_F64, st))
+    nat.check(lib.mb_serialize_chunks(payload.data_ptr(), n, nb, n, out.data_ptr(), stride, ws.data_ptr(), wsb,
+                                      info.data_ptr(), st))
+    infos = info.cpu().numpy().view(INFO_DTYPE)
+
+    def fetch(k: int) -> bytes:
+        ln = int(infos["out_len"][k])
+        return out[k * stride:k * stride + ln].cpu().numpy().tobytes()
+
+    return infos, fetch
+
+
 def render_level_to_store(store: DataStore, level: int, mrd: int, chunks=None, *, definition: int = nat.CHUNK_DEFINITION,
-                          skip_completed: bool = True) -> int:
+                          skip_completed: bool = True, batch: int = 16) -> int:
     """Render chunks of `level` (all level^2 of them unless `chunks` is given, e.g. an iterator
-    that pops indices from the in-box work-stealing queue) straight into the store.  Chunks the
-    index already holds are skipped, like the Distributer's resume (Distributer.cs:165-175)."""
+    that pops indices from the in-box work-stealing queue) straight into the store, `batch` chunks
+    per set of launches.  Chunks the index already holds are skipped, like the Distributer's resume
+    (Distributer.cs:165-175)."""
     have = {(l, r, i) for (l, r, i, _t, _f) in store.completed()} if skip_completed else set()
     if chunks is None:
         # Distributer.TryGetNextNeededWorkload order (Distributer.cs:335-353): indexReal outer, indexImag inner
         chunks = ((ir, ii) for ir in range(level) for ii in range(level))
-    buf = np.empty(int(definition) * int(definition) + 1, dtype=np.uint8)
-    done = 0
-    for (ir, ii) in chunks:
-        if (level, ir, ii) in have:
-            continue
-        etype, blob = render_serialized(level, mrd, ir, ii, definition=definition, out=buf)
-        store.save(level, ir, ii, etype, blob if etype == ENTRY_REGULAR else None)
-        done += 1
-    return done
+    todo = [(ir, ii) for (ir, ii) in chunks if (level, ir, ii) not in have]
+    for first in range(0, len(todo), max(1, batch)):
+        part = todo[first:first + max(1, batch)]
+        infos, fetch = render_serialized_batch([(level, mrd, ir, ii) for (ir, ii) in part], definition=definition)
+        for k, (ir, ii) in enumerate(part):
+            etype = int(infos["entry_type"][k])
+            store.save(level, ir, ii, etype, fetch(k) if etype == ENTRY_REGULAR else None)
+    return len(todo)

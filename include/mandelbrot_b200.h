@@ -153,17 +153,30 @@ int mb_classify_u8(const uint8_t *payload_dev, size_t n, uint32_t *flags_dev, vo
 /* ---- DataChunk serialisation on the device ---------------------------------- */
 /*
  * Replaces DataChunk.Serialize (DataChunk.cs:173-206) with its two serializers
- * (DataChunkSerializer.cs:29-49 raw, :51-100 RLE): out = 1 codec byte (0x00 raw / 0x01 RLE) +
- * either the n payload bytes or one (uint32 LE runLength, uint8 value) record per maximal run;
- * RLE only when strictly shorter.  out_dev needs n + 1 bytes; *out_len_dev (device uint64)
- * receives the serialised length.  workspace_dev: mb_serialize_workspace_bytes(n) bytes.
- * n < 2^32.  Asynchronous on `stream`.
+ * (DataChunkSerializer.cs:29-49 raw, :51-100 RLE) for a BATCH of equally sized chunks in one set
+ * of launches: chunk c is read from payloads_dev + c*payload_stride (n bytes) and written to
+ * out_dev + c*out_stride as 1 codec byte (0x00 raw / 0x01 RLE) + either the n payload bytes or
+ * one (uint32 LE runLength, uint8 value) record per maximal run; RLE only when strictly shorter.
+ * info_dev[c] receives the serialised length, the run count and the IndexEntry type the server
+ * would derive (DataChunk.cs:82,87; DataStorage.cs:71-84).  out_stride >= n + 1, a multiple of 16
+ * for speed (mb_serialize_out_stride).  n < 2^32, n_chunks <= 65535.  Asynchronous on `stream`.
  */
-size_t mb_serialize_workspace_bytes(size_t n);
-int mb_serialize_chunk(const uint8_t *payload_dev, size_t n, uint8_t *out_dev, size_t out_capacity,
-                       void *workspace_dev, size_t workspace_bytes, uint64_t *out_len_dev,
-                       void *stream);
-/* host-pointer form (copies in, serialises on the device, copies the result out; synchronous) */
+typedef struct mb_chunk_info {
+    uint64_t out_len;      /* serialised bytes, codec byte included */
+    uint32_t runs;
+    uint32_t codec;        /* 0 raw, 1 RLE */
+    uint32_t entry_type;   /* 0 Regular, 1 Never (all 0), 2 Immediate (all 1) */
+    uint32_t first_value;
+    uint32_t reserved[2];
+} mb_chunk_info;           /* 32 bytes */
+
+size_t mb_serialize_out_stride(size_t n);
+size_t mb_serialize_workspace_bytes(size_t n, uint32_t n_chunks);
+int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks,
+                        size_t payload_stride, uint8_t *out_dev, size_t out_stride,
+                        void *workspace_dev, size_t workspace_bytes, mb_chunk_info *info_dev,
+                        void *stream);
+/* host-pointer form for one chunk (copies in, serialises on the device, copies out; synchronous) */
 int mb_serialize_chunk_host(const uint8_t *payload_host, size_t n, uint8_t *out_host,
                             size_t out_capacity, uint64_t *out_len);
 

@@ -118,11 +118,27 @@ def test_native_chunk_serialized_and_classified(gpu, codec, oracle):
 
 
 @pytest.mark.gpu
+def test_batched_serializer_and_classification(gpu, codec, oracle):
+    """Several chunks per set of launches; entry types fall out of the run counts."""
+    from distributedmandelbrot_b200.storage import render_serialized_batch
+    d = 160
+    wl = [(8, 300, 0, 0), (8, 64, 3, 4), (10, 300, 3, 5), (4, 256, 1, 2), (6, 256, 0, 0), (3, 90, 1, 1), (16, 500, 5, 8)]
+    infos, fetch = render_serialized_batch(wl, definition=d)
+    for k, w in enumerate(wl):
+        payload = oracle.process_workload(*w, d)
+        want = codec.serialize(payload)
+        assert int(infos["entry_type"][k]) == codec.entry_type(payload), w
+        assert int(infos["out_len"][k]) == len(want) and int(infos["codec"][k]) == want[0]
+        assert fetch(k) == want, w
+    assert sorted(set(infos["entry_type"].tolist())) == [0, 1, 2]
+
+
+@pytest.mark.gpu
 def test_render_level_to_store(gpu, codec, oracle, tmp_path):
     from distributedmandelbrot_b200.storage import DataStore, render_level_to_store
     st = DataStore(str(tmp_path))
     level, mrd, d = 4, 40, 96
-    assert render_level_to_store(st, level, mrd, definition=d) == 16
+    assert render_level_to_store(st, level, mrd, definition=d, batch=5) == 16
     entries = st.completed()
     assert [(e[1], e[2]) for e in entries] == [(ir, ii) for ir in range(4) for ii in range(4)]   # Distributer order
     for (lv, ir, ii, etype, name) in entries:
