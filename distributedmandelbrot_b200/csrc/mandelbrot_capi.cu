@@ -407,6 +407,54 @@ int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real
     return MB_OK;
 }
 
+// ---- in-box dispatch loop (8e) ----------------------------------------------------------------
+
+int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_tile *tiles, uint32_t n_tiles,
+                           uint32_t bands_per_claim, uint32_t depth, int32_t *out_dev, int dtype, void *stream,
+                           uint32_t *claimed, uint32_t max_claims, uint32_t *n_claims, uint32_t *n_stolen)
+{
+    if (!q || !tiles || !out_dev || !claimed || !n_claims) return fail(MB_ERR_INVALID, "NULL argument");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(MB_ERR_INVALID, "rank %u out of range", rank);
+    if (bands_per_claim == 0) bands_per_claim = 1;
+    if (depth == 0) depth = 1;
+    if (depth > 16) depth = 16;
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ring[16];
+    for (uint32_t k = 0; k < depth; ++k) MB_CUDA(cudaEventCreateWithFlags(&ring[k], cudaEventDisableTiming));
+    uint32_t claims = 0, stolen_total = 0;
+    int result = MB_OK;
+    for (;;) {
+        const int64_t remaining = mb_wsq_remaining(q);
+        uint32_t want = (uint32_t)(remaining / ((int64_t)n_ranks * 8));
+        if (want > bands_per_claim) want = bands_per_claim;
+        if (want == 0) want = 1;
+        uint32_t first = 0, got = 0, stolen = 0;
+        const int pr = mb_wsq_pop(q, rank, want, &first, &got, &stolen);
+        if (pr < 0) { result = pr; break; }
+        if (pr == 0) break;
+        if ((uint64_t)first + got > n_tiles) { result = fail(MB_ERR_STATE, "queue handed out tile %u of %u", first + got - 1, n_tiles); break; }
+        if (claims >= max_claims) { result = fail(MB_ERR_INVALID, "claimed[] too small (%u claims)", max_claims); break; }
+        if (claims >= depth) {                              // at most `depth` launches in flight
+            cudaError_t e = cudaEventSynchronize(ring[claims % depth]);
+            if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e)); break; }
+        }
+        if ((result = mb_render_counts(tiles + first, got, out_dev, dtype, stream))) break;
+        cudaError_t e = cudaEventRecord(ring[claims % depth], st);
+        if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e)); break; }
+        claimed[2 * claims] = first;
+        claimed[2 * claims + 1] = got;
+        ++claims;
+        stolen_total += stolen;
+    }
+    for (uint32_t k = 0; k < depth; ++k) cudaEventDestroy(ring[k]);
+    *n_claims = claims;
+    if (n_stolen) *n_stolen = stolen_total;
+    return result;
+}
+
 // ---- serialisation (f2) --------------------------------------------------------------------
 
 static size_t codec_blocks(size_t n) { return (n + mbc::kSegment - 1) / mbc::kSegment; }

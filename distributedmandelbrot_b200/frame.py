@@ -138,6 +138,19 @@ class FrameRenderer:
         self.claimed, self.steals = [], 0
         inflight = []
         cuda = self.device.type == "cuda"
+        if cuda:
+            # the same loop in native code (mb_frame_render_stolen): ~10 us instead of ~60 us per claim
+            cap = self.spec.n_bands
+            buf = (C.c_uint32 * (2 * cap))()
+            n_claims, n_stolen = C.c_uint32(), C.c_uint32()
+            nat.check(nat.lib().mb_frame_render_stolen(
+                queue._h, self.rank, self.world, self.tiles, self.spec.n_bands, self.bands_per_claim, self.depth,
+                self.out.data_ptr(), nat.DTYPES[self.spec.dtype], torch.cuda.current_stream(self.device).cuda_stream,
+                buf, cap, C.byref(n_claims), C.byref(n_stolen)))
+            self.claimed = coalesce([(buf[2 * k], buf[2 * k + 1]) for k in range(n_claims.value)])
+            self.steals = n_stolen.value
+            self.launches += n_claims.value
+            return
         while True:
             # guided self-scheduling: full-size claims while plenty is left, single bands at the end
             want = max(1, min(self.bands_per_claim, queue.remaining() // (self.world * 8)))

@@ -236,6 +236,20 @@ int64_t mb_wsq_remaining(mb_wsq *q);
 int mb_wsq_close(mb_wsq *q);
 int mb_wsq_unlink(const char *name);
 
+/*
+ * The per-GPU dispatch loop of the in-box frame renderer, in native code (a Python loop costs
+ * ~60 us per claim, which shows once a band of exterior pixels renders in 10 us): claim up to
+ * `bands_per_claim` consecutive tiles for `rank` (shrinking to single tiles near the end:
+ * guided self-scheduling), launch them with mb_render_counts on `stream`, keep at most `depth`
+ * launches in flight, repeat until the queue is drained.  claimed[2*k], claimed[2*k+1] receive
+ * the (first, count) of claim k (capacity max_claims pairs); *n_claims, *n_stolen count them.
+ * Returns after the last launch is ENQUEUED (not finished).
+ */
+int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_tile *tiles,
+                           uint32_t n_tiles, uint32_t bands_per_claim, uint32_t depth,
+                           int32_t *out_dev, int dtype, void *stream, uint32_t *claimed,
+                           uint32_t max_claims, uint32_t *n_claims, uint32_t *n_stolen);
+
 /* ---- roofline denominators, measured on the bound device ------------------------------ */
 /*
  * Dependency-free DFMA (dtype F64) / FFMA (F32) issue-rate microbenchmark: every SM runs
