@@ -187,7 +187,7 @@ def main() -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    fr = FrameRenderer(spec, device=local, rank=rank, world=world, bands_per_claim=4, depth=3)
+    fr = FrameRenderer(spec, device=local, rank=rank, world=world, bands_per_claim=4, depth=6)
     queue = None
     if world > 1:
         qn = queue_name()

@@ -44,6 +44,7 @@ struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
     cudaStream_t stream = nullptr;      // private non-blocking stream for the host-buffer entry points
+    cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};   // concurrent launch lanes of the dispatch loop
     void *scratch = nullptr;            // device output buffer of the host-buffer entry points
     size_t scratch_bytes = 0;
     std::mutex mu;
@@ -193,6 +194,7 @@ int mb_init(int device)
             return fail(MB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         c.sm_count = prop.multiProcessorCount;
         MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        for (auto &ln : c.lanes) MB_CUDA(cudaStreamCreateWithFlags(&ln, cudaStreamNonBlocking));
         // descriptor batches use cudaMallocAsync: keep the pool's memory across synchronisations
         // instead of returning it to the OS (default threshold 0 re-allocates on every call)
         cudaMemPool_t pool;
@@ -214,6 +216,7 @@ void mb_shutdown(void)
         cudaSetDevice(d);
         if (c.scratch) cudaFree(c.scratch);
         if (c.stream) cudaStreamDestroy(c.stream);
+        for (auto &ln : c.lanes) { if (ln) cudaStreamDestroy(ln); ln = nullptr; }
         c.scratch = nullptr;
         c.scratch_bytes = 0;
         c.stream = nullptr;
@@ -422,7 +425,16 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
     int rc = current_ctx(&c);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaEvent_t ring[16];
+    // Claims go round-robin onto kLanes internal streams so that the drain of one launch (a few
+    // long-running CTAs at the set boundary) overlaps the head of the next; in one stream every
+    // launch boundary would idle most of the GPU.  Tiles never overlap, so concurrency is safe.
+    // The lanes start after everything already enqueued on `stream`, and `stream` waits for the
+    // lanes before this function returns, so callers keep plain stream semantics.
+    constexpr uint32_t kLanes = 4;
+    cudaEvent_t ring[16], fence;
+    MB_CUDA(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+    MB_CUDA(cudaEventRecord(fence, st));
+    for (uint32_t k = 0; k < kLanes; ++k) MB_CUDA(cudaStreamWaitEvent(c->lanes[k], fence, 0));
     for (uint32_t k = 0; k < depth; ++k) MB_CUDA(cudaEventCreateWithFlags(&ring[k], cudaEventDisableTiming));
     uint32_t claims = 0, stolen_total = 0;
     int result = MB_OK;
@@ -441,15 +453,20 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
             cudaError_t e = cudaEventSynchronize(ring[claims % depth]);
             if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e)); break; }
         }
-        if ((result = mb_render_counts(tiles + first, got, out_dev, dtype, stream))) break;
-        cudaError_t e = cudaEventRecord(ring[claims % depth], st);
+        cudaStream_t lane = c->lanes[claims % kLanes];
+        if ((result = mb_render_counts(tiles + first, got, out_dev, dtype, lane))) break;
+        cudaError_t e = cudaEventRecord(ring[claims % depth], lane);
         if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e)); break; }
         claimed[2 * claims] = first;
         claimed[2 * claims + 1] = got;
         ++claims;
         stolen_total += stolen;
     }
+    for (uint32_t k = 0; k < kLanes; ++k) {                 // join the lanes back into the caller's stream
+        if (cudaEventRecord(fence, c->lanes[k]) == cudaSuccess) cudaStreamWaitEvent(st, fence, 0);
+    }
     for (uint32_t k = 0; k < depth; ++k) cudaEventDestroy(ring[k]);
+    cudaEventDestroy(fence);
     *n_claims = claims;
     if (n_stolen) *n_stolen = stolen_total;
     return result;
