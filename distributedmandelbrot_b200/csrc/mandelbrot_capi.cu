@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "chunk_codec.cuh"
 #include "escape_kernels.cuh"
@@ -19,6 +20,9 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_device = -1;
+#ifdef MB_TUNING_VARIANTS
+int g_variant = 0;
+#endif
 
 int fail(int code, const char *fmt, ...)
 {
@@ -129,6 +133,31 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
         MB_CUDA(cudaMemcpyAsync(tiles_dev, tiles, bytes, cudaMemcpyHostToDevice, st));
     }
 
+#ifdef MB_TUNING_VARIANTS
+    // development-only sweep of launch shapes (scripts/tune_variants.py); never built by default
+    if (g_variant != 0 && dtype == MB_DTYPE_F64) {
+        const int v = g_variant;
+        auto go = [&](auto head, auto wx, auto wy, auto minc) -> int {
+            constexpr int H = decltype(head)::value, WX = decltype(wx)::value, WY = decltype(wy)::value, MC = decltype(minc)::value;
+            const uint32_t cw = WX * mbk::kWarpW, ch = WY * mbk::kWarpH;
+            const uint32_t per_tile = ((mw + cw - 1) / cw) * ((mh + ch - 1) / ch);
+            for (uint32_t first = 0; first < n_tiles; first += kMaxGridY) {
+                const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
+                args.dev = tiles_dev ? tiles_dev + first : nullptr;
+                mbk::escape_tiles_kernel<double, OutT, H, WX, WY, MC><<<dim3(per_tile, cnt, 1), WX * WY * 32, 0, st>>>(args, out_dev);
+                MB_CUDA(cudaGetLastError());
+            }
+            return MB_OK;
+        };
+        using std::integral_constant;
+#define MB_V(id, H, WX, WY, MC) if (v == id) { rc = go(integral_constant<int, H>{}, integral_constant<int, WX>{}, integral_constant<int, WY>{}, integral_constant<int, MC>{}); }
+        MB_V(1, 16, 2, 2, 12) MB_V(2, 64, 2, 2, 12) MB_V(3, 32, 1, 2, 24) MB_V(4, 32, 2, 4, 6) MB_V(5, 32, 4, 1, 12)
+        MB_V(6, 32, 1, 1, 32) MB_V(7, 32, 2, 2, 8) MB_V(8, 0, 2, 2, 12) MB_V(9, 32, 4, 2, 6)
+#undef MB_V
+        if (tiles_dev) MB_CUDA(cudaFreeAsync(tiles_dev, st));
+        return rc;
+    }
+#endif
     const uint32_t ctas_per_tile = ((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
     for (uint32_t first = 0; first < n_tiles; first += kMaxGridY) {
         const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
@@ -162,6 +191,10 @@ int grid_for(size_t n, int sm_count)
 }  // namespace
 
 extern "C" {
+
+#ifdef MB_TUNING_VARIANTS
+void mb_internal_set_variant(int v) { g_variant = v; }
+#endif
 
 // shared with tile_wsq.cpp so that queue errors are readable through mb_last_error()
 int mb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
