@@ -158,19 +158,26 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
         return rc;
     }
 #endif
-    const uint32_t ctas_per_tile = ((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
-    for (uint32_t first = 0; first < n_tiles; first += kMaxGridY) {
-        const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
-        const dim3 grid(ctas_per_tile, cnt, 1), block(kWX * kWY * 32, 1, 1);
-        args.dev = tiles_dev ? tiles_dev + first : nullptr;
-        if (dtype == MB_DTYPE_F64)
-            mbk::escape_tiles_kernel<double, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
-        else
-            mbk::escape_tiles_kernel<float, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
-        MB_CUDA(cudaGetLastError());
+    const uint64_t ctas64 = (uint64_t)((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
+    cudaError_t err = cudaSuccess;
+    if (ctas64 > 0x7fffffffull) {
+        rc = fail(MB_ERR_INVALID, "tile too large for one launch (%llu CTAs)", (unsigned long long)ctas64);
+    } else {
+        const uint32_t ctas_per_tile = (uint32_t)ctas64;
+        for (uint32_t first = 0; first < n_tiles && err == cudaSuccess; first += kMaxGridY) {
+            const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
+            const dim3 grid(ctas_per_tile, cnt, 1), block(kWX * kWY * 32, 1, 1);
+            args.dev = tiles_dev ? tiles_dev + first : nullptr;
+            if (dtype == MB_DTYPE_F64)
+                mbk::escape_tiles_kernel<double, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
+            else
+                mbk::escape_tiles_kernel<float, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
+            err = cudaGetLastError();
+        }
+        if (err != cudaSuccess) rc = fail(MB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     }
-    if (tiles_dev) MB_CUDA(cudaFreeAsync(tiles_dev, st));
-    return MB_OK;
+    if (tiles_dev) cudaFreeAsync(tiles_dev, st);      // also on the error paths: never leak the descriptor batch
+    return rc;
 }
 
 // strict binary64 host arithmetic: `volatile` pins each rounding even if someone adds -mfma

@@ -108,7 +108,9 @@ double mb_tile_coord(const mb_tile *t, int axis /*0 = real, 1 = imag*/, uint32_t
  * counts for `n_tiles` tiles, written to out_dev.  One CUDA thread per pixel; coordinates are
  * generated in-kernel from the descriptors (nothing but 88 bytes per tile is read).
  * Count semantics (.py:44-68): z0 = c; n = 1..mrd-1: z <- z^2 + c; first n with |z|^2 >= 4,
- * else 0.
+ * else 0.  The caller guarantees that every tile's output range
+ * [out_offset, out_offset + (h-1)*out_pitch + w) lies inside out_dev and that tiles of one launch
+ * do not overlap; tiles of one launch may differ in size, mrd and chunk.
  */
 int mb_render_counts(const mb_tile *tiles, uint32_t n_tiles, int32_t *out_dev, int dtype,
                      void *stream);

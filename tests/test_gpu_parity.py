@@ -291,3 +291,36 @@ def test_process_workloads_pipeline_equals_single_calls(gpu, oracle):
     worker.process_workloads(wl[:2], definition=d, consume=lambda w, p: seen.append((w, int(p.sum()))))
     assert [s[0] for s in seen] == wl[:2] and seen[0][1] == int(got[0].sum())
     assert worker.process_workloads([], definition=d) == []
+
+
+def test_full_size_f32_chunk_properties(gpu, oracle):
+    """cfg3 (FP32, mrd 4096) at the native 4096^2 chunk size: determinism, tiling invariance,
+    fused uint8 == epilogue(int32), and strided rows against the binary32 oracle."""
+    from distributedmandelbrot_b200.frame import CONFIGS
+    spec = CONFIGS["cfg3"]
+    d, mrd = spec.definition, spec.mrd
+    chunk = gpu.chunk_geometry(spec.level, 1, 1, d, mrd)
+    a = _render(gpu, [chunk], d * d, dtype="f32")
+    assert np.array_equal(a, _render(gpu, [chunk], d * d, dtype="f32"))
+    bands = [chunk.sub(0, y, d, 256, y * d, d) for y in range(0, d, 256)]
+    assert np.array_equal(a, _render(gpu, bands, d * d, dtype="f32"))
+    assert np.array_equal(_render(gpu, [chunk], d * d, dtype="f32", u8=True), oracle.counts_to_u8(a, mrd))
+    for y in range(0, d, 373):
+        want = oracle.render_chunk_counts(spec.level, mrd, 1, 1, d, dtype="f32", x0=0, y0=y, w=d, h=1)
+        assert np.array_equal(a.reshape(d, d)[y], want[0]), y
+
+
+def test_cfg5_geometry_rows_vs_oracle(gpu, oracle):
+    """cfg5 (level 4,000,000, mrd 50000): pixel pitch 2.4e-10, coordinates differ in the last few
+    bits -- rows of a boundary chunk and of the frame's corner chunks against the oracle."""
+    from distributedmandelbrot_b200.frame import CONFIGS
+    spec = CONFIGS["cfg5"]
+    d, mrd = spec.definition, spec.mrd
+    for (ir, ii, rows) in [(spec.ir0 + 2, spec.ii0 + 5, (0, 1777, 4095)), (spec.ir0, spec.ii0, (4095,)),
+                           (spec.ir0 + 7, spec.ii0 + 7, (0,))]:
+        chunk = gpu.chunk_geometry(spec.level, ir, ii, d, mrd)
+        tiles = [chunk.sub(0, y, d, 1, k * d, d) for k, y in enumerate(rows)]
+        got = _render(gpu, tiles, len(rows) * d).reshape(len(rows), d)
+        for k, y in enumerate(rows):
+            want = oracle.render_chunk_counts(spec.level, mrd, ir, ii, d, x0=0, y0=y, w=d, h=1)
+            assert np.array_equal(got[k], want[0]), (ir, ii, y)
