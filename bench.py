@@ -104,6 +104,15 @@ def cpu_sample(spec, d: int, threads: int):
     return useful, time.perf_counter() - t0
 
 
+def cpu_quota() -> str:
+    """cgroup CPU quota of this container, if any (a 128-thread box may grant far fewer core-seconds)."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        return "unlimited" if q == "max" else f"{int(q) / int(per):.1f} cores"
+    except Exception:  # noqa: BLE001
+        return "unknown"
+
+
 def cpu_baseline(spec, budget_s: float = 15.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
@@ -117,7 +126,7 @@ def cpu_baseline(spec, budget_s: float = 15.0):
     return {"value": useful / sec / 1e9, "unit": METRIC, "cores": threads, "kind": "port",
             "sample": f"same frame ({spec.name}), all {spec.n_chunks} chunks at reduced definition d={d} "
                       f"({useful:.4g} pixel-iterations in {sec:.1f} s); oracle/mandel_oracle.c, gcc -O2 -ffp-contract=off, "
-                      f"{threads} pthreads, one dynamic (chunk,row) queue"}, d
+                      f"{threads} pthreads, one dynamic (chunk,row) queue; cgroup cpu quota: {cpu_quota()}"}, d
 
 
 def run_reference(args, spec):
