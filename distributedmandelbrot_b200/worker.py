@@ -294,9 +294,22 @@ def main(argv=None) -> None:
     ap.add_argument("--device", type=int, default=None)
     ap.add_argument("--pipeline", type=int, default=0, metavar="DEPTH",
                     help="keep DEPTH leases in flight (0 = one at a time, like the reference)")
+    ap.add_argument("--gpus", type=int, default=0, metavar="N",
+                    help="start one worker process per GPU for devices 0..N-1 (today: N copies of the reference worker)")
     args = ap.parse_args(argv)
     addr = args.addr if args.addr is not None else input("Server Addr> ")
     port = args.port if args.port is not None else int(input("Server Port> "))
+    if args.gpus > 0:
+        # one process per GPU, exactly like running N reference workers against the same Distributer
+        import subprocess
+        import sys
+        procs = [subprocess.Popen([sys.executable, "-m", "distributedmandelbrot_b200.worker", "--addr", addr,
+                                   "--port", str(port), "--device", str(k), "--pipeline", str(args.pipeline)])
+                 for k in range(args.gpus)]
+        codes = [p.wait() for p in procs]
+        if any(codes):
+            raise SystemExit(f"worker exit codes: {codes}")
+        return
     nat.ensure_init(args.device)
     if args.pipeline > 0:
         run_pipelined(addr, port, depth=max(2, args.pipeline))
