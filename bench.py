@@ -352,7 +352,7 @@ def main() -> None:
                           "steps": args.e2e_steps, "s_per_step": e2e_s}
         else:
             out["e2e"] = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # timed on rank 0 at N = 1 only
             out["cpu_baseline"], _d = cpu_baseline(spec)
         print(json.dumps(out), flush=True)
 
