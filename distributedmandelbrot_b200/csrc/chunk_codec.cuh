@@ -21,8 +21,8 @@
 namespace mbc {
 
 constexpr int kThreads = 256;
-constexpr int kBytesPerThread = 64;                     // four 128-bit loads per thread
-constexpr int kSegment = kThreads * kBytesPerThread;   // 16 KiB of payload per CTA
+constexpr int kBytesPerThread = 16;
+constexpr int kSegment = kThreads * kBytesPerThread;   // 4096 payload bytes per CTA
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -50,16 +50,15 @@ struct Batch {
     uint32_t nblocks;             // CTAs per chunk
 };
 
-// 64-bit mask: bit j set iff byte j of this thread's 64-byte span starts a run
-__device__ __forceinline__ unsigned long long start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint8_t *bytes)
+// 16-bit mask: bit j set iff byte j of this thread's 16-byte span starts a run
+__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint8_t *bytes)
 {
-    unsigned long long mask = 0;
+    uint32_t mask = 0;
     if (base >= n) return 0;
     const bool full = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0);
     if (full) {
-#pragma unroll
-        for (int q = 0; q < kBytesPerThread / 16; ++q)
-            reinterpret_cast<uint4 *>(bytes)[q] = reinterpret_cast<const uint4 *>(p + base)[q];
+        const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+        reinterpret_cast<uint4 *>(bytes)[0] = v;
     } else {
 #pragma unroll
         for (int j = 0; j < kBytesPerThread; ++j) bytes[j] = (base + j < n) ? p[base + j] : 0;
@@ -67,7 +66,7 @@ __device__ __forceinline__ unsigned long long start_mask(const uint8_t *__restri
     uint8_t prev = base ? p[base - 1] : 0;
 #pragma unroll
     for (int j = 0; j < kBytesPerThread; ++j) {
-        if (base + j < n && (base + j == 0 || bytes[j] != prev)) mask |= 1ull << j;
+        if (base + j < n && (base + j == 0 || bytes[j] != prev)) mask |= 1u << j;
         prev = bytes[j];
     }
     return mask;
@@ -104,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) count_run_starts(const Batch b)
     const size_t n = b.n;
     alignas(16) uint8_t bytes[kBytesPerThread];
     const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
-    const uint32_t c = __popcll(start_mask(p, base, n, bytes));
+    const uint32_t c = __popc(start_mask(p, base, n, bytes));
     uint32_t total;
     block_exclusive_scan(c, &total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
@@ -162,35 +161,32 @@ __global__ void __launch_bounds__(kThreads) scatter_runs(const Batch b)
     if (meta->codec == 0) {
         // RawSerializer (DataChunkSerializer.cs:34-37): out[1 + i] = p[i].  The destination is
         // 1 byte off alignment, so build aligned 32-bit words from two neighbouring source words.
-        for (int q = 0; q < kBytesPerThread / 16; ++q) {
-            const size_t sb = base + (size_t)q * 16;            // 16-byte sub-span
-            if (sb >= n) break;
-            const bool fast = sb + 16 <= n && ((reinterpret_cast<uintptr_t>(p + sb) & 15u) == 0) &&
-                              ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-            if (fast) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(p + sb);
-                const uint32_t before = sb ? (uint32_t)p[sb - 1] : (uint32_t)out[0];   // header byte for the very first word
-                uint4 w;
-                w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
-                w.y = __byte_perm(v.x, v.y, 0x6543);          // {v.x.b3, v.y.b0, v.y.b1, v.y.b2}
-                w.z = __byte_perm(v.y, v.z, 0x6543);
-                w.w = __byte_perm(v.z, v.w, 0x6543);
-                *reinterpret_cast<uint4 *>(out + sb) = w;     // out[sb .. sb+15] = {p[sb-1], p[sb .. sb+14]}
-                if (sb + 16 == n) out[n] = (uint8_t)(v.w >> 24);                       // last payload byte
-            } else {
-                // a word-building neighbour to the left leaves out[sb] (= p[sb-1]) to this sub-span
-                if (sb) out[sb] = p[sb - 1];
-                for (int j = 0; j < 16 && sb + j < n; ++j) out[1 + sb + j] = p[sb + j];
-            }
+        if (base >= n) return;
+        const bool fast = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+        if (fast) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+            const uint32_t before = base ? (uint32_t)p[base - 1] : (uint32_t)out[0];   // header byte for the very first word
+            uint4 w;
+            w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
+            w.y = __byte_perm(v.x, v.y, 0x6543);          // {v.x.b3, v.y.b0, v.y.b1, v.y.b2}
+            w.z = __byte_perm(v.y, v.z, 0x6543);
+            w.w = __byte_perm(v.z, v.w, 0x6543);
+            *reinterpret_cast<uint4 *>(out + base) = w;   // covers out[base .. base+15] = {p[base-1], p[base .. base+14]}
+            if (base + kBytesPerThread == n) out[n] = (uint8_t)(v.w >> 24);           // last payload byte
+        } else {
+            // a word-building neighbour to the left leaves out[base] (= p[base-1]) to this thread
+            if (base) out[base] = p[base - 1];
+            for (int j = 0; j < kBytesPerThread && base + j < n; ++j) out[1 + base + j] = p[base + j];
         }
         return;
     }
-    const unsigned long long mask = start_mask(p, base, n, bytes);
+    const uint32_t mask = start_mask(p, base, n, bytes);
     uint32_t total;
-    uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(__popcll(mask), &total);
+    uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(__popc(mask), &total);
 #pragma unroll
     for (int j = 0; j < kBytesPerThread; ++j) {
-        if (mask & (1ull << j)) {
+        if (mask & (1u << j)) {
             starts[r] = (uint32_t)(base + j);
             out[1 + (size_t)r * 5 + 4] = bytes[j];        // runValue (DataChunkSerializer.cs:84,98)
             ++r;
