@@ -170,3 +170,69 @@ def render_level_to_store(store: DataStore, level: int, mrd: int, chunks=None, *
             etype = int(infos["entry_type"][k])
             store.save(level, ir, ii, etype, fetch(k) if etype == ENTRY_REGULAR else None)
     return len(todo)
+
+
+def parse_levels(text: str):
+    """`-l level:mrd,level:mrd,...` exactly like the server's CLI (Program.cs:227-257)."""
+    out = []
+    for part in text.split(","):
+        level, mrd = part.split(":")
+        level, mrd = int(level), int(mrd)
+        if level <= 0 or mrd <= 0:
+            raise ValueError("levels and maximum recursion depths must be positive")
+        out.append((level, mrd))
+    return out
+
+
+def main(argv=None) -> None:
+    """In-box replacement for `DistributedMandelbrot -l ... -o DIR` + N workers: renders the level
+    settings straight into DIR/Data.  Under torchrun the chunks of each level are handed to the
+    ranks by the shared-memory work-stealing queue (one process per GPU); alone it uses GPU 0.
+
+        python -m distributedmandelbrot_b200.storage -l 4:256,10:1024 -o /srv/mandelbrot/
+        python -m torch.distributed.run --nproc-per-node 8 -m distributedmandelbrot_b200.storage -l 20:1024 -o DIR
+    """
+    import argparse
+    ap = argparse.ArgumentParser(description=main.__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("-l", "--levels", required=True, help="level:mrd[,level:mrd...] (Program.cs:227-257)")
+    ap.add_argument("-o", "--output", default=".", help="parent of the Data/ directory (Program.cs:384-398)")
+    ap.add_argument("--definition", type=int, default=nat.CHUNK_DEFINITION)
+    ap.add_argument("--batch", type=int, default=16)
+    args = ap.parse_args(argv)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    nat.ensure_init(local)
+    store = DataStore(args.output)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    for k, (level, mrd) in enumerate(parse_levels(args.levels)):
+        order = [(ir, ii) for ir in range(level) for ii in range(level)]     # Distributer.cs:335-353
+        if world == 1:
+            n = render_level_to_store(store, level, mrd, order, definition=args.definition, batch=args.batch)
+        else:
+            from .frame import queue_name
+            qn = f"{queue_name()}_s{k}"
+            q = nat.TileQueue(qn, world, len(order), create=True) if rank == 0 else None
+            dist.barrier()
+            if rank != 0:
+                q = nat.TileQueue(qn)
+
+            def mine():
+                while (g := q.pop(rank, args.batch)) is not None:
+                    yield from order[g[0]:g[0] + g[1]]
+
+            n = render_level_to_store(store, level, mrd, mine(), definition=args.definition, batch=args.batch)
+            dist.barrier()
+            q.close()
+        print(f"[rank {rank}] level {level} mrd {mrd}: {n} chunk(s) written to {store.dir}", flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,3 +150,24 @@ def test_render_level_to_store(gpu, codec, oracle, tmp_path):
         else:
             assert name is None
     assert render_level_to_store(st, level, mrd, definition=d) == 0                                # resume: nothing left
+
+
+def test_levels_cli_syntax():
+    from distributedmandelbrot_b200.storage import parse_levels
+    assert parse_levels("4:256,10:1024,20:1024") == [(4, 256), (10, 1024), (20, 1024)]      # launchSettings.json:5
+    with pytest.raises(ValueError):
+        parse_levels("4:0")
+
+
+@pytest.mark.gpu
+def test_storage_cli_single_gpu(gpu, codec, oracle, tmp_path):
+    from distributedmandelbrot_b200 import storage
+    storage.main(["-l", "2:30,3:20", "-o", str(tmp_path), "--definition", "64", "--batch", "3"])
+    entries = storage.DataStore(str(tmp_path)).completed()
+    assert [(e[0], e[1], e[2]) for e in entries] == [(2, r, i) for r in range(2) for i in range(2)] + \
+                                                   [(3, r, i) for r in range(3) for i in range(3)]
+    for (lv, ir, ii, etype, name) in entries:
+        payload = oracle.process_workload(lv, 30 if lv == 2 else 20, ir, ii, 64)
+        assert etype == codec.entry_type(payload)
+        if etype == 0:
+            assert open(tmp_path / "Data" / name, "rb").read() == codec.serialize(payload)

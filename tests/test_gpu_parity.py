@@ -324,3 +324,35 @@ def test_cfg5_geometry_rows_vs_oracle(gpu, oracle):
         for k, y in enumerate(rows):
             want = oracle.render_chunk_counts(spec.level, mrd, ir, ii, d, x0=0, y0=y, w=d, h=1)
             assert np.array_equal(got[k], want[0]), (ir, ii, y)
+
+
+def test_cfg4_full_frame_properties(gpu, oracle):
+    """BASELINE config 4 at its FULL size (65536^2, mrd 10000, 16 GiB of counts): the one-launch
+    frame equals the same frame rendered chunk by chunk (tiling/launch invariance), the per-chunk
+    useful-iteration sums add up to the frame total (a checksum of checksums), every count is in
+    [0, mrd-1], and sampled rows agree with the oracle."""
+    import torch
+    from distributedmandelbrot_b200.frame import CONFIGS, FrameRenderer
+    spec = CONFIGS["cfg4"]
+    d, mrd, n = spec.definition, spec.mrd, spec.definition ** 2
+    fr = FrameRenderer(spec, device=0)
+    fr.render_all()
+    torch.cuda.synchronize()
+    total = fr.useful_iterations()
+    assert total == 27_914_249_068_737            # measured on the first parity-green build; any change is a regression
+    assert int(fr.out.min()) >= 0 and int(fr.out.max()) <= mrd - 1
+    per_chunk = torch.empty(n, dtype=torch.int32, device="cuda")
+    acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lib = gpu.lib()
+    for c, (ir, ii) in enumerate(spec.chunk_indices()):
+        t = gpu.chunk_geometry(spec.level, ir, ii, d, mrd)
+        gpu.check(lib.mb_render_counts(gpu.tile_array([t]), 1, per_chunk.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+        assert torch.equal(per_chunk, fr.out[c * n:(c + 1) * n]), (ir, ii)
+        gpu.check(lib.mb_useful_iterations(per_chunk.data_ptr(), n, mrd, acc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert int(acc.item()) == total
+    frame = fr.out.view(spec.n_chunks, d, d)
+    for c in range(5, spec.n_chunks, 37):
+        ir, ii = spec.chunk_indices()[c]
+        y = (c * 613) % d
+        want = oracle.render_chunk_counts(spec.level, mrd, ir, ii, d, x0=0, y0=y, w=d, h=1)
+        assert np.array_equal(frame[c, y].cpu().numpy(), want[0]), (ir, ii, y)
