@@ -45,6 +45,8 @@ template <> struct Ops<double> {
     // m >= 4.0 for finite m >= 0  <=>  hi32(m) >= hi32(4.0)
     static __device__ __forceinline__ bool escaped(double m) { return __double2hiint(m) >= 0x40100000; }
     static __device__ __forceinline__ double coord(double v) { return v; }
+    static __device__ __forceinline__ bool ordinary(double cr, double ci) { return fabs(cr) <= 4.0 && fabs(ci) <= 4.0; }
+    static __device__ __forceinline__ bool ge4(double m) { return m >= 4.0; }     // IEEE compare: false for NaN
 };
 
 template <> struct Ops<float> {
@@ -55,6 +57,8 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ bool escaped(float m) { return __float_as_int(m) >= 0x40800000; }
     // Appendix A.5: the binary64 linspace value rounded once to binary32
     static __device__ __forceinline__ float coord(double v) { return __double2float_rn(v); }
+    static __device__ __forceinline__ bool ordinary(float cr, float ci) { return fabsf(cr) <= 4.0f && fabsf(ci) <= 4.0f; }
+    static __device__ __forceinline__ bool ge4(float m) { return m >= 4.0f; }
 };
 
 // ---- deferred escape test ---------------------------------------------------------------------
@@ -124,6 +128,17 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
     int n = 0;                                 // updates performed
     int result = 0;                            // 0 = never escaped (.py:68)
     bool done = !active || left <= 0;
+    if (!done && !O::ordinary(cr, ci)) {
+        // Coordinates outside [-4, 4]^2 (only reachable through calc_mb_value or a hand-made tile:
+        // DataChunks live in [-2, 2]^2), including inf and NaN: none of the bounds above hold, so
+        // evaluate .py:44-68 literally with an IEEE compare (NaN >= 4 is false, as in numpy/C#).
+        for (; left > 0; --left) {
+            update<Real>(x, y, xx, yy, cr, ci);
+            ++n;
+            if (O::ge4(O::add(xx, yy))) { result = n; break; }
+        }
+        done = true;
+    }
     for (;;) {
         if (!done) {
             if (left < K) {

@@ -181,6 +181,20 @@ def test_points_on_the_radius_2_circle(gpu, oracle):
         assert np.array_equal(got, oracle.render_chunk_counts(level, mrd, ir, ii, d)), (level, ir, ii)
 
 
+def test_calc_mb_value_non_finite_and_huge_inputs(gpu, oracle):
+    """The ufunc boundary accepts any float64: inf, NaN and coordinates far outside the plane must
+    give what the literal loop gives (e.g. NaN >= 4 is False forever -> 0)."""
+    from distributedmandelbrot_b200 import worker
+    vals = [0.0, 1.0, -3.0, 4.0, 4.000001, 1e10, -1e154, 1e200, 1.7e308, np.inf, -np.inf, np.nan, 5e-324, 2.5]
+    r = np.array([a for a in vals for _ in vals])
+    i = np.array([b for _ in vals for b in vals])
+    with np.errstate(all="ignore"):
+        for mrd in (2, 3, 40, 300):
+            got = worker.calc_mb_value(r, i, mrd)
+            want = np.array([oracle.escape_f64(a, b, mrd) for a, b in zip(r, i)], np.int32)
+            assert np.array_equal(got, want), (mrd, np.flatnonzero(got != want)[:5])
+
+
 def test_u8_epilogue_standalone_and_fused(gpu, golden_meta, golden_arrays):
     import torch
     for rec in golden_meta["u8"]:
