@@ -101,8 +101,8 @@ int check_tiles(const mb_tile *tiles, uint32_t n_tiles, uint32_t *max_w, uint32_
 // Launch shape.  CTA = 2 x 2 warps of 8x4 pixels (16 x 8 pixels, 128 threads): small CTAs
 // release their SM slots soon after their own pixels finish, which matters because escape
 // times differ by orders of magnitude between neighbouring CTAs at the set boundary.
-// <= 40 registers/thread and 12 CTAs/SM = 48 resident warps/SM; the FP64 pipe saturates with
-// ~3 warps per sub-partition, so occupancy beyond that buys nothing.
+// 34 registers/thread, 12 CTAs/SM = 48 resident warps/SM; the FP64 pipe saturates with ~3 warps
+// per sub-partition, so occupancy beyond that buys nothing (profiles/r01_tuning_sweep.txt).
 constexpr int kWX = 2, kWY = 2, kMinCtas = 12, kHead = 32;
 constexpr uint32_t kCtaW = kWX * mbk::kWarpW, kCtaH = kWY * mbk::kWarpH;
 constexpr uint32_t kMaxGridY = 65535;
@@ -130,7 +130,11 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
     } else {
         const size_t bytes = sizeof(mb_tile) * (size_t)n_tiles;
         MB_CUDA(cudaMallocAsync((void **)&tiles_dev, bytes, st));
-        MB_CUDA(cudaMemcpyAsync(tiles_dev, tiles, bytes, cudaMemcpyHostToDevice, st));
+        const cudaError_t ce = cudaMemcpyAsync(tiles_dev, tiles, bytes, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) {
+            cudaFreeAsync(tiles_dev, st);
+            return fail(MB_ERR_CUDA, "descriptor upload failed: %s", cudaGetErrorString(ce));
+        }
     }
 
 #ifdef MB_TUNING_VARIANTS
