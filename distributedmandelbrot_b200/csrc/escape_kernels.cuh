@@ -131,9 +131,16 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
     if (!done && !O::ordinary(cr, ci)) {
         // Coordinates outside [-4, 4]^2 (only reachable through calc_mb_value or a hand-made tile:
         // DataChunks live in [-2, 2]^2), including inf and NaN: none of the bounds above hold, so
-        // evaluate .py:44-68 literally with an IEEE compare (NaN >= 4 is false, as in numpy/C#).
+        // evaluate .py:44-68 literally with an IEEE compare (NaN >= 4 is false, as in numpy/C#)
+        // and the literal (2*x)*y: 2*x overflows for |x| > 8.99e307, where fma(x*y, 2, ci) differs
+        // (e.g. c = 1.7e308 + 0i: (2x)*y = inf*0 = NaN, so the reference never "escapes").
         for (; left > 0; --left) {
-            update<Real>(x, y, xx, yy, cr, ci);
+            const Real a = O::sub(xx, yy);
+            const Real b2 = O::mul(O::add(x, x), y);
+            x = O::add(a, cr);
+            y = O::add(b2, ci);
+            xx = O::mul(x, x);
+            yy = O::mul(y, y);
             ++n;
             if (O::ge4(O::add(xx, yy))) { result = n; break; }
         }
