@@ -62,12 +62,12 @@ template <> struct Ops<float> {
 };
 
 // ---- deferred escape test ---------------------------------------------------------------------
-// On B200 a warp-wide FP64 instruction holds an SM sub-partition's issue port for 2 cycles and
-// every other instruction for 1 (measured: profiles/), so the loop is ISSUE bound: testing
-// |z|^2 >= 4 after every update costs 7 FP64 + 3 other instructions = 17 cycles per
-// pixel-iteration (82 % of the DFMA peak, which is what the checked loop reaches).  The steady
-// state below therefore runs K updates with NO test -- and without the magnitude add, which only
-// the test consumes: 6 FP64 instructions per update -- then tests once.  If the orbit escaped
+// On B200 an SM sub-partition has 16 FP64 lanes: a warp-wide FP64 instruction occupies the pipe
+// for 2 cycles, and every other instruction costs an issue slot that overlaps it only partly
+// (measured: ~0.6-1 cycle each, profiles/).  Testing |z|^2 >= 4 after every update costs 7 FP64 +
+// 3 other instructions per pixel-iteration and reached 82 % of the DFMA peak.  The steady state
+// below therefore runs K updates with NO test -- and without the magnitude add, which only the
+// test consumes: 6 FP64 instructions per update -- then tests once (ncu: FP64 pipe 97 % busy).  If the orbit escaped
 // somewhere inside the block, the block is REPLAYED from its saved start with a test after every
 // update, so the reported n is the exact first n with fl(fl(x^2)+fl(y^2)) >= 4, as .py:62-66.
 //
