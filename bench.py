@@ -172,6 +172,9 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: nccl = one batched send/recv gather to rank 0; p2p = kernels store directly "
+                         "into rank 0's frame buffer over NVLink peer memory (no gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     spec = get_spec(args.workload)
@@ -183,7 +186,7 @@ def main() -> None:
     import torch.distributed as dist
     from distributedmandelbrot_b200 import _native as nat
     from distributedmandelbrot_b200 import worker
-    from distributedmandelbrot_b200.frame import FrameRenderer, queue_name
+    from distributedmandelbrot_b200.frame import FrameRenderer, queue_name, shared_frame_buffer
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -196,7 +199,10 @@ def main() -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    fr = FrameRenderer(spec, device=local, rank=rank, world=world, bands_per_claim=4, depth=6)
+    shared_out, close_shared = (None, None)
+    if world > 1 and args.gather == "p2p":
+        shared_out, close_shared = shared_frame_buffer(spec, rank, local)
+    fr = FrameRenderer(spec, device=local, rank=rank, world=world, bands_per_claim=4, depth=6, out=shared_out)
     queue = None
     if world > 1:
         qn = queue_name()
@@ -211,7 +217,9 @@ def main() -> None:
             fr.render_all()                # every band in one launch
         else:
             fr.render_stolen(queue)        # work-stealing dispatch ...
-            fr.gather_to_root()            # ... and the one collective: bands -> rank 0
+            if shared_out is None:
+                fr.gather_to_root()        # ... and the one collective: bands -> rank 0
+            # (p2p: the stores already landed in rank 0's buffer; the barrier + synchronize below close the step)
 
     def rearm():
         if world > 1:
@@ -331,7 +339,8 @@ def main() -> None:
                        "pixels": spec.pixels, "useful_pixel_iterations": useful,
                        "mean_iterations_per_pixel": useful / spec.pixels, "band_rows": spec.band_rows,
                        "parallelism": "1 GPU, one launch over all bands" if world == 1 else
-                                      f"{world} GPUs, shm work-stealing bands + one batched NCCL send/recv gather to rank 0",
+                                      f"{world} GPUs, shm work-stealing bands + " + ("one batched NCCL send/recv gather to rank 0" if shared_out is None
+                                                                                      else "kernel stores directly into rank 0's buffer over NVLink peer memory"),
                        "l2": f"kernel reads only 88-byte descriptors; output {spec.pixels * 4 / 2**30:.1f} GiB int32 per step >> 126 MB L2 (no L2 flush needed)",
                        "steals": int(steals.item())},
             "clocks": clocks,
@@ -359,6 +368,11 @@ def main() -> None:
     if queue is not None:
         dist.barrier()
         queue.close()
+    if close_shared is not None:
+        del fr
+        torch.cuda.synchronize()
+        dist.barrier()
+        close_shared()
     if world > 1:
         dist.destroy_process_group()
 

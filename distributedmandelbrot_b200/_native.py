@@ -105,6 +105,10 @@ SIGNATURES = {
     "mb_frame_render_stolen": (_int, [_vp, _u32, _u32, _PT, _u32, _u32, _u32, _vp, _int, _vp, C.POINTER(_u32), _u32,
                                       C.POINTER(_u32), C.POINTER(_u32)]),
     "mb_wsq_unlink": (_int, [C.c_char_p]),
+    "mb_peer_alloc": (_int, [_sz, C.POINTER(_vp), _vp]),
+    "mb_peer_open": (_int, [_vp, C.POINTER(_vp)]),
+    "mb_peer_close": (_int, [_vp]),
+    "mb_peer_free": (_int, [_vp]),
     "mb_measure_fma_peak": (_int, [_int, _int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "mb_measure_pipe_rate": (_int, [_int, _int, _int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
 }

@@ -454,6 +454,54 @@ int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real
     return MB_OK;
 }
 
+// ---- peer-shared frame buffer (8e, alternative to the gather) ------------------------------------
+
+int mb_peer_alloc(size_t bytes, void **dev_ptr, void *handle_out)
+{
+    if (!dev_ptr || !handle_out || bytes == 0) return fail(MB_ERR_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MB_PEER_HANDLE_BYTES, "handle size");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    void *p = nullptr;
+    MB_CUDA(cudaMalloc(&p, bytes));                      // plain cudaMalloc: IPC needs a whole allocation
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(MB_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return MB_OK;
+}
+
+int mb_peer_open(const void *handle, void **dev_ptr)
+{
+    if (!handle || !dev_ptr) return fail(MB_ERR_INVALID, "NULL argument");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    MB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MB_OK;
+}
+
+int mb_peer_close(void *dev_ptr)
+{
+    if (!dev_ptr) return MB_OK;
+    MB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return MB_OK;
+}
+
+int mb_peer_free(void *dev_ptr)
+{
+    if (!dev_ptr) return MB_OK;
+    MB_CUDA(cudaFree(dev_ptr));
+    return MB_OK;
+}
+
 // ---- in-box dispatch loop (8e) ----------------------------------------------------------------
 
 int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_tile *tiles, uint32_t n_tiles,

@@ -252,6 +252,20 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
                            int32_t *out_dev, int dtype, void *stream, uint32_t *claimed,
                            uint32_t max_claims, uint32_t *n_claims, uint32_t *n_stolen);
 
+/* ---- frame buffer shared between the GPU processes of one box (peer memory over NVLink) ------- */
+/*
+ * Alternative to the final gather: rank 0 allocates the frame buffer (mb_peer_alloc) and exports
+ * a 64-byte handle; the other ranks open it (mb_peer_open) and pass the returned pointer as
+ * out_dev to mb_render_counts / mb_frame_render_stolen, so the kernel's 128-bit count stores land
+ * directly in rank 0's HBM over NVLink/NVSwitch -- the "collective" is fused into the kernel's
+ * epilogue and nothing is left to gather.  (CUDA IPC; same box only.)
+ */
+#define MB_PEER_HANDLE_BYTES 64
+int mb_peer_alloc(size_t bytes, void **dev_ptr, void *handle_out);
+int mb_peer_open(const void *handle, void **dev_ptr);
+int mb_peer_close(void *dev_ptr);     /* for pointers from mb_peer_open */
+int mb_peer_free(void *dev_ptr);      /* for pointers from mb_peer_alloc */
+
 /* ---- roofline denominators, measured on the bound device ------------------------------ */
 /*
  * Dependency-free DFMA (dtype F64) / FFMA (F32) issue-rate microbenchmark: every SM runs
