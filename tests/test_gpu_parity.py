@@ -370,3 +370,24 @@ def test_cfg4_full_frame_properties(gpu, oracle):
         y = (c * 613) % d
         want = oracle.render_chunk_counts(spec.level, mrd, ir, ii, d, x0=0, y0=y, w=d, h=1)
         assert np.array_equal(frame[c, y].cpu().numpy(), want[0]), (ir, ii, y)
+
+
+def test_peer_frame_buffer_alloc_and_render(gpu, oracle):
+    """The exporter side of the peer-memory frame buffer (mb_peer_alloc + zero-copy torch view);
+    the importer side needs a second process/GPU and is exercised by `bench.py --gather p2p`."""
+    import torch
+    from distributedmandelbrot_b200.frame import _RawCudaArray
+    d = 128
+    ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    gpu.check(gpu.lib().mb_peer_alloc(d * d * 4, C.byref(ptr), handle))
+    try:
+        assert any(handle)
+        t = torch.as_tensor(_RawCudaArray(ptr.value, d * d), device="cuda")
+        assert t.data_ptr() == ptr.value and t.dtype == torch.int32
+        chunk = gpu.chunk_geometry(10, 3, 5, d, 500)
+        gpu.check(gpu.lib().mb_render_counts(gpu.tile_array([chunk]), 1, ptr, 0, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(t.cpu().numpy().reshape(d, d), oracle.render_chunk_counts(10, 500, 3, 5, d))
+        del t
+    finally:
+        gpu.check(gpu.lib().mb_peer_free(ptr))
