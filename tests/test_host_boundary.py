@@ -107,3 +107,44 @@ def test_product_package_never_touches_the_oracle():
                 txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "mandel_oracle" not in txt, f
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_header_is_plain_c_and_links_from_c(native, tmp_path):
+    """The boundary is a C ABI: include/mandelbrot_b200.h must compile as C99 and a C program must
+    link against the library and call the host-only entry points (no GPU needed)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "mandelbrot_b200.h"
+int main(void) {
+    mb_tile t;
+    if (mb_abi_version() != MB_ABI_VERSION) return 1;
+    if (sizeof(mb_tile) != 88 || sizeof(mb_chunk_info) != 32) return 2;
+    if (mb_chunk_geometry(4, 1, 2, 512, 256, &t) != MB_OK) return 3;
+    if (t.start_r != -1.0 || t.start_i != 0.0 || t.stop_r != 0.0 || t.w != 512) return 4;
+    if (mb_tile_coord(&t, 0, 511) != t.stop_r || mb_tile_coord(&t, 0, 0) != t.start_r) return 5;
+    if (mb_chunk_geometry(0, 0, 0, 512, 256, &t) != MB_ERR_INVALID) return 6;      /* "Level must be positive" */
+    if (strstr(mb_last_error(), "Level must be positive") == NULL) return 7;
+    mb_wsq *q = NULL; uint32_t first, got, stolen;
+    if (mb_wsq_create("/mbq_c_abi_test", 2, 10, &q) != MB_OK) return 8;
+    if (mb_wsq_pop(q, 1, 3, &first, &got, &stolen) != 1 || first != 5 || got != 3) return 9;
+    if (mb_wsq_remaining(q) != 7) return 10;
+    mb_wsq_close(q); mb_wsq_unlink("/mbq_c_abi_test");
+    printf("ok\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "use_abi"
+    so = native.library_path()
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), so, f"-Wl,-rpath,{os.path.dirname(so)}"])
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
