@@ -50,26 +50,51 @@ struct Batch {
     uint32_t nblocks;             // CTAs per chunk
 };
 
-// 16-bit mask: bit j set iff byte j of this thread's 16-byte span starts a run
-__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint8_t *bytes)
+// 4-bit mask of the bytes that differ between two words (SIMD byte compare, no per-byte loop)
+__device__ __forceinline__ uint32_t differ4(uint32_t a, uint32_t b)
 {
-    uint32_t mask = 0;
+    const uint32_t ne = __vcmpne4(a, b) & 0x01010101u;          // bit 0 of each byte = "differs"
+    return ((ne * 0x01020408u) >> 24) & 0xfu;                   // gather bits 0, 8, 16, 24 -> 0..3
+}
+
+// 16-bit mask: bit j set iff byte j of this thread's 16-byte span starts a run
+// (p[i] != p[i-1]; i = 0 always starts one).  `v` receives the 16 payload bytes (zero-padded).
+__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint4 &v)
+{
+    v = make_uint4(0, 0, 0, 0);
     if (base >= n) return 0;
+    const uint32_t prev = base ? (uint32_t)p[base - 1] : 0u;
     const bool full = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0);
+    uint32_t mask;
     if (full) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
-        reinterpret_cast<uint4 *>(bytes)[0] = v;
+        v = *reinterpret_cast<const uint4 *>(p + base);
+        // the same 16 bytes shifted up by one byte, `prev` entering at the bottom
+        const uint32_t s0 = __byte_perm(prev, v.x, 0x6540), s1 = __byte_perm(v.x, v.y, 0x6543);
+        const uint32_t s2 = __byte_perm(v.y, v.z, 0x6543), s3 = __byte_perm(v.z, v.w, 0x6543);
+        mask = differ4(v.x, s0) | (differ4(v.y, s1) << 4) | (differ4(v.z, s2) << 8) | (differ4(v.w, s3) << 12);
     } else {
+        uint8_t bytes[kBytesPerThread];
+        mask = 0;
+        uint8_t pb = (uint8_t)prev;
 #pragma unroll
-        for (int j = 0; j < kBytesPerThread; ++j) bytes[j] = (base + j < n) ? p[base + j] : 0;
+        for (int j = 0; j < kBytesPerThread; ++j) {
+            bytes[j] = (base + j < n) ? p[base + j] : 0;
+            if (base + j < n && bytes[j] != pb) mask |= 1u << j;
+            pb = bytes[j];
+        }
+        v.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+        v.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | ((uint32_t)bytes[7] << 24);
+        v.z = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | ((uint32_t)bytes[11] << 24);
+        v.w = bytes[12] | (bytes[13] << 8) | (bytes[14] << 16) | ((uint32_t)bytes[15] << 24);
     }
-    uint8_t prev = base ? p[base - 1] : 0;
-#pragma unroll
-    for (int j = 0; j < kBytesPerThread; ++j) {
-        if (base + j < n && (base + j == 0 || bytes[j] != prev)) mask |= 1u << j;
-        prev = bytes[j];
-    }
+    if (base == 0) mask |= 1u;
     return mask;
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint4 &v, int j)
+{
+    const uint32_t w = j < 8 ? (j < 4 ? v.x : v.y) : (j < 12 ? v.z : v.w);
+    return (w >> (8 * (j & 3))) & 0xffu;
 }
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
@@ -101,9 +126,9 @@ __global__ void __launch_bounds__(kThreads) count_run_starts(const Batch b)
     const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
     uint32_t *__restrict__ block_counts = b.counts + blockIdx.y * b.counts_stride;
     const size_t n = b.n;
-    alignas(16) uint8_t bytes[kBytesPerThread];
+    uint4 v;
     const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
-    const uint32_t c = __popc(start_mask(p, base, n, bytes));
+    const uint32_t c = __popc(start_mask(p, base, n, v));
     uint32_t total;
     block_exclusive_scan(c, &total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
@@ -156,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) scatter_runs(const Batch b)
     uint32_t *__restrict__ starts = b.starts + blockIdx.y * b.starts_stride;
     uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
     const size_t n = b.n;
-    alignas(16) uint8_t bytes[kBytesPerThread];
+    uint4 v;
     const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
     if (meta->codec == 0) {
         // RawSerializer (DataChunkSerializer.cs:34-37): out[1 + i] = p[i].  The destination is
@@ -165,7 +190,7 @@ __global__ void __launch_bounds__(kThreads) scatter_runs(const Batch b)
         const bool fast = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
                           ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
         if (fast) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+            v = *reinterpret_cast<const uint4 *>(p + base);
             const uint32_t before = base ? (uint32_t)p[base - 1] : (uint32_t)out[0];   // header byte for the very first word
             uint4 w;
             w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
@@ -181,16 +206,15 @@ __global__ void __launch_bounds__(kThreads) scatter_runs(const Batch b)
         }
         return;
     }
-    const uint32_t mask = start_mask(p, base, n, bytes);
+    uint32_t mask = start_mask(p, base, n, v);
     uint32_t total;
     uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(__popc(mask), &total);
-#pragma unroll
-    for (int j = 0; j < kBytesPerThread; ++j) {
-        if (mask & (1u << j)) {
-            starts[r] = (uint32_t)(base + j);
-            out[1 + (size_t)r * 5 + 4] = bytes[j];        // runValue (DataChunkSerializer.cs:84,98)
-            ++r;
-        }
+    while (mask) {                                        // one trip per run start, not per byte
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        starts[r] = (uint32_t)(base + j);
+        out[1 + (size_t)r * 5 + 4] = (uint8_t)byte_of(v, j);   // runValue (DataChunkSerializer.cs:84,98)
+        ++r;
     }
 }
 
