@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gpixel-iterations/s"
 OPS_PER_PIXEL_ITERATION = 7          # FP64/FP32-pipe instructions the rounding sequence needs
+# Sum of useful pixel-iterations of the full frames as produced by the parity-tested single-GPU path
+# (tests/test_gpu_parity.py::test_cfg4_full_frame_properties; cfg5/cfg2/cfg3 recorded from the same build).
+# A multi-GPU run (work stealing + gather) must land on the same number: a fast frame that differs is wrong.
+EXPECTED_USEFUL = {"cfg4": 27_914_249_068_737, "cfg5": 6_306_807_763_045, "cfg2": 1_666_561_672, "cfg3": 104_413_119_766}
 NOMINAL_FMA_TERA = {"f64": 148 * 64 * 1.965e9 / 1e12, "f32": 148 * 128 * 1.965e9 / 1e12}
 
 
@@ -315,6 +319,9 @@ def main() -> None:
             dist.barrier()
             cq.close()
 
+    if rank == 0 and args.workload in EXPECTED_USEFUL and useful != EXPECTED_USEFUL[args.workload]:
+        raise SystemExit(f"PARITY GUARD: frame {args.workload} sums to {useful} useful pixel-iterations, "
+                         f"expected {EXPECTED_USEFUL[args.workload]} -- the rendered frame is wrong")
     if rank == 0:
         value = useful / (ms_per_step * 1e-3) / 1e9
         peak_fma, _ = nat.measure_pipe_rate(spec.dtype, 0, 16384)        # tera FMA-pipe lane-ops/s, live
@@ -342,7 +349,8 @@ def main() -> None:
                                       f"{world} GPUs, shm work-stealing bands + " + ("one batched NCCL send/recv gather to rank 0" if shared_out is None
                                                                                       else "kernel stores directly into rank 0's buffer over NVLink peer memory"),
                        "l2": f"kernel reads only 88-byte descriptors; output {spec.pixels * 4 / 2**30:.1f} GiB int32 per step >> 126 MB L2 (no L2 flush needed)",
-                       "steals": int(steals.item())},
+                       "steals": int(steals.item()),
+                       "parity_guard": "frame sum equals the parity-tested single-GPU value" if args.workload in EXPECTED_USEFUL else "none for this workload"},
             "clocks": clocks,
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "fp64_pipe" if spec.dtype == "f64" else "fp32_pipe",
