@@ -190,7 +190,7 @@ def main() -> None:
     import torch.distributed as dist
     from distributedmandelbrot_b200 import _native as nat
     from distributedmandelbrot_b200 import worker
-    from distributedmandelbrot_b200.frame import FrameRenderer, queue_name, shared_frame_buffer
+    from distributedmandelbrot_b200.frame import FrameRenderer, probe_chunk_costs, queue_name, shared_frame_buffer
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -284,13 +284,15 @@ def main() -> None:
             if rank != 0:
                 cq = nat.TileQueue(cqn)
 
+        order = list(range(len(wl_all)))
+
         def source():
             if cq is None:
                 yield from wl_all
                 return
             while (g := cq.pop(rank, 1)) is not None:
                 for k in range(g[0], g[0] + g[1]):
-                    yield wl_all[k]
+                    yield wl_all[order[k]]
 
         worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None)   # warm the pinned ring
         total_s = 0.0
@@ -308,6 +310,11 @@ def main() -> None:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
+            if world > 1:
+                # expensive chunks first (a 2 ms low-resolution probe, inside the timed region; every rank
+                # computes the same deterministic order)
+                costs = probe_chunk_costs(spec, device=local)
+                order = sorted(range(len(wl_all)), key=lambda k: -costs[k])
             worker.process_workloads(source(), definition=spec.definition, consume=consume)
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)

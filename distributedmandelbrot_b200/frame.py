@@ -204,6 +204,28 @@ class FrameRenderer:
         return int(acc.item())
 
 
+def probe_chunk_costs(spec: FrameSpec, samples: int = 48, device: int = 0):
+    """Cheap cost estimate per chunk: render every chunk's window at `samples` x `samples` (one launch,
+    ~2 ms for 256 chunks) and sum the useful iterations.  Used to hand out the expensive chunks first
+    (longest-processing-time-first) when whole chunks are the unit of dispatch, e.g. behind the
+    worker API where a DataChunk cannot be split; the Distributer's own order (Distributer.cs:335-353)
+    ignores cost and leaves one 50 000-iteration chunk as the tail."""
+    import torch
+    dev = torch.device("cuda", nat.ensure_init(device))
+    n = samples * samples
+    tiles = []
+    for c, (ir, ii) in enumerate(spec.chunk_indices()):
+        t = nat.chunk_geometry(spec.level, ir, ii, samples, spec.mrd)
+        t.out_offset = c * n
+        tiles.append(t)
+    out = torch.empty(spec.n_chunks * n, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().mb_render_counts(nat.tile_array(tiles), len(tiles), out.data_ptr(), nat.DTYPES[spec.dtype],
+                                         torch.cuda.current_stream(dev).cuda_stream))
+    counts = out.view(spec.n_chunks, n)
+    never = max(spec.mrd - 1, 0)
+    return torch.where(counts == 0, torch.full_like(counts, never), counts).sum(dim=1, dtype=torch.int64).cpu().tolist()
+
+
 class _RawCudaArray:
     """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface)."""
 

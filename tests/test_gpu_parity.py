@@ -391,3 +391,19 @@ def test_peer_frame_buffer_alloc_and_render(gpu, oracle):
         del t
     finally:
         gpu.check(gpu.lib().mb_peer_free(ptr))
+
+
+def test_probe_chunk_costs_ranks_chunks(gpu):
+    """The low-resolution cost probe orders chunks like their true cost (used for LPT dispatch)."""
+    from distributedmandelbrot_b200.frame import CONFIGS, FrameRenderer, probe_chunk_costs
+    spec = CONFIGS["cfg2"]
+    costs = probe_chunk_costs(spec, samples=32)
+    fr = FrameRenderer(spec, device=0)
+    fr.render_all()
+    full = fr.out.view(spec.n_chunks, -1)
+    import torch
+    true = torch.where(full == 0, torch.full_like(full, spec.mrd - 1), full).sum(dim=1, dtype=torch.int64).cpu().numpy()
+    est = np.array(costs, dtype=np.float64) * (spec.definition / 32) ** 2
+    heavy = np.argsort(-true)[:20]
+    assert set(np.argsort(-est)[:30]) >= set(heavy[:10])          # the heaviest chunks are found
+    assert np.corrcoef(est, true)[0, 1] > 0.95
