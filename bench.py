@@ -295,6 +295,8 @@ def main() -> None:
                     yield wl_all[order[k]]
 
         worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None)   # warm the pinned ring
+        if world > 1:
+            probe_chunk_costs(spec, device=local)                                                   # ... and the probe's torch ops
         total_s = 0.0
         nbytes = 0
 
