@@ -316,7 +316,15 @@ def main() -> None:
                 # expensive chunks first (a 2 ms low-resolution probe, inside the timed region; every rank
                 # computes the same deterministic order)
                 costs = probe_chunk_costs(spec, device=local)
-                order = sorted(range(len(wl_all)), key=lambda k: -costs[k])
+                lpt = sorted(range(len(wl_all)), key=lambda k: -costs[k])
+                # the queue starts from a static contiguous split: deal the LPT order round-robin so that
+                # every rank's own range is "its share, expensive first" and steals take cheap chunks
+                order, n_all = [], len(wl_all)
+                for r in range(world):
+                    lo, hi = n_all * r // world, n_all * (r + 1) // world
+                    order += [lpt[j * world + r] for j in range(hi - lo) if j * world + r < n_all]
+                missing = [k for k in lpt if k not in set(order)]
+                order += missing
             worker.process_workloads(source(), definition=spec.definition, consume=consume)
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
