@@ -127,7 +127,7 @@ def cpu_baseline(spec, budget_s: float = 15.0):
         scale = max(1.5, min(4.0, (budget_s / max(sec, 1e-3)) ** 0.5 * 0.8))
         d = int(min(1024, max(d + 8, d * scale)))
         useful, sec = cpu_sample(spec, d, threads)
-    return {"value": useful / sec / 1e9, "unit": METRIC, "cores": threads, "kind": "port",
+    return {"value": useful / sec / 1e9, "unit": METRIC, "cores": threads, "cpu_quota": cpu_quota(), "kind": "port",
             "sample": f"same frame ({spec.name}), all {spec.n_chunks} chunks at reduced definition d={d} "
                       f"({useful:.4g} pixel-iterations in {sec:.1f} s); oracle/mandel_oracle.c, gcc -O2 -ffp-contract=off, "
                       f"{threads} pthreads, one dynamic (chunk,row) queue; cgroup cpu quota: {cpu_quota()}"}, d
