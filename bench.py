@@ -232,7 +232,7 @@ def main() -> None:
                 queue.reset(spec.n_bands)
             dist.barrier()
 
-    for _ in range(args.warmup):
+    for _ in range(max(1, args.warmup)):   # at least one untimed frame: the metric's numerator is read from it
         rearm()
         step()
     torch.cuda.synchronize()
