@@ -288,6 +288,72 @@ int mbo_render_frame(uint32_t level, uint32_t ir0, uint32_t ii0, uint32_t blocks
     return 0;
 }
 
+/* Empirical check of the property the CUDA kernel's deferred escape test relies on
+ * (csrc/escape_kernels.cuh): once the computed |z|^2 reaches 4, it stays >= 4 and finite for the
+ * next `extra` updates.  Counts the points that violate it.  Points with | |c|^2 - 4 | <= band are
+ * skipped (the kernel never defers those).  Strict arithmetic as everywhere in this file. */
+uint64_t mbo_sticky_violations(const double *r, const double *im, size_t n, int32_t mrd, int extra, double band)
+{
+    uint64_t bad = 0;
+    for (size_t k = 0; k < n; ++k) {
+        const double c0 = r[k], c1 = im[k];
+        volatile double q0 = c0 * c0, q1 = c1 * c1;
+        volatile double q = (q0 + q1) - 4.0;
+        if (q <= band && q >= -band) continue;
+        double z0 = c0, z1 = c1;
+        int left = -1;                      /* updates still to verify after the first escape */
+        for (int32_t it = 1; it < mrd; ++it) {
+            double a = z0 * z0, b = z1 * z1;
+            double sq0 = a - b;
+            double t = 2.0 * z0;
+            double sq1 = t * z1;
+            z0 = sq0 + c0;
+            z1 = sq1 + c1;
+            double m0 = z0 * z0, m1 = z1 * z1;
+            double m = m0 + m1;
+            if (left < 0) {
+                if (m >= 4.0) left = extra;
+            } else {
+                if (!(m >= 4.0) || !(m < 1.7976931348623157e308)) { ++bad; break; }
+            }
+            if (left == 0) break;
+            if (left > 0) --left;
+        }
+    }
+    return bad;
+}
+
+/* binary32 counterpart: the kernel's block-end test there is `!(m < 4)` (overflow to inf/NaN counts
+ * as escaped), blocks of 16, band 2^-9 on |c|^2. */
+uint64_t mbo_sticky_violations_f32(const double *r, const double *im, size_t n, int32_t mrd, int extra, float band)
+{
+    uint64_t bad = 0;
+    for (size_t k = 0; k < n; ++k) {
+        const float c0 = (float)r[k], c1 = (float)im[k];
+        volatile float q0 = c0 * c0, q1 = c1 * c1;
+        volatile float q = (q0 + q1) - 4.0f;
+        if (q <= band && q >= -band) continue;
+        float z0 = c0, z1 = c1;
+        int left = -1;
+        for (int32_t it = 1; it < mrd; ++it) {
+            float a = z0 * z0, b = z1 * z1;
+            float sq0 = a - b;
+            float t = 2.0f * z0;
+            float sq1 = t * z1;
+            z0 = sq0 + c0;
+            z1 = sq1 + c1;
+            float m0 = z0 * z0, m1 = z1 * z1;
+            float m = m0 + m1;
+            if (left < 0) {
+                if (m >= 4.0f) left = extra;
+            } else if (m < 4.0f) { ++bad; break; }
+            if (left == 0) break;
+            if (left > 0) --left;
+        }
+    }
+    return bad;
+}
+
 uint64_t mbo_useful_iterations(const int32_t *counts, size_t n, int32_t mrd)
 {
     uint64_t s = 0;

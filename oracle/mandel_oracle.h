@@ -69,6 +69,12 @@ int mbo_process_workload(uint32_t level, int32_t mrd, uint32_t index_real, uint3
 int mbo_render_frame(uint32_t level, uint32_t ir0, uint32_t ii0, uint32_t blocks, uint32_t d,
                      int32_t mrd, int dtype, int threads, int32_t *out, uint64_t *useful);
 
+/* number of points whose computed |z|^2 drops below 4 (or overflows) within `extra` updates after
+ * first reaching 4 -- the property behind the kernel's deferred escape test; expected 0 */
+uint64_t mbo_sticky_violations(const double *r, const double *im, size_t n, int32_t mrd, int extra, double band);
+
+uint64_t mbo_sticky_violations_f32(const double *r, const double *im, size_t n, int32_t mrd, int extra, float band);
+
 void mbo_counts_to_u8(const int32_t *counts, uint8_t *out, size_t n, int32_t mrd);
 
 /* sum over pixels of (n ? n : mrd-1): the unit of the Gpixel-iterations/s metric */

@@ -54,6 +54,10 @@ def lib() -> C.CDLL:
         L.mbo_process_workload.restype = C.c_int
         L.mbo_render_frame.argtypes = [u32, u32, u32, u32, u32, i32, C.c_int, C.c_int, pi32, C.POINTER(u64)]
         L.mbo_render_frame.restype = C.c_int
+        L.mbo_sticky_violations.argtypes = [pd, pd, sz, i32, C.c_int, d]
+        L.mbo_sticky_violations.restype = u64
+        L.mbo_sticky_violations_f32.argtypes = [pd, pd, sz, i32, C.c_int, C.c_float]
+        L.mbo_sticky_violations_f32.restype = u64
         L.mbo_counts_to_u8.argtypes = [pi32, pu8, sz, i32]
         L.mbo_counts_to_u8.restype = None
         L.mbo_useful_iterations.argtypes = [pi32, sz, i32]
@@ -125,6 +129,20 @@ def render_frame(level, ir0, ii0, blocks, d, mrd, dtype="f64", threads=0, want_c
     if rc != 0:
         raise ValueError(f"mbo_render_frame failed rc={rc}")
     return out, int(useful.value)
+
+
+def sticky_violations(r, i, mrd: int, extra: int = 7, band: float = 2.0 ** -36) -> int:
+    """Points where the computed |z|^2 falls below 4 (or overflows) within `extra` updates of first
+    reaching 4; the CUDA kernel's deferred escape test relies on this never happening."""
+    r = np.ascontiguousarray(r, dtype=np.float64).ravel()
+    i = np.ascontiguousarray(i, dtype=np.float64).ravel()
+    return int(lib().mbo_sticky_violations(_p(r, C.c_double), _p(i, C.c_double), r.size, mrd, extra, band))
+
+
+def sticky_violations_f32(r, i, mrd: int, extra: int = 15, band: float = 2.0 ** -9) -> int:
+    r = np.ascontiguousarray(r, dtype=np.float64).ravel()
+    i = np.ascontiguousarray(i, dtype=np.float64).ravel()
+    return int(lib().mbo_sticky_violations_f32(_p(r, C.c_double), _p(i, C.c_double), r.size, mrd, extra, band))
 
 
 def counts_to_u8(counts: np.ndarray, mrd: int) -> np.ndarray:

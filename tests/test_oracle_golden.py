@@ -120,3 +120,41 @@ def test_frame_driver_equals_per_chunk(oracle):
     assert useful == oracle.useful_iterations(counts, 200)
     c32, _ = oracle.render_frame(4, 1, 1, 2, 33, 300, dtype="f32")
     assert np.array_equal(c32[3], oracle.render_chunk_counts(4, 300, 2, 2, 33, dtype="f32"))
+
+
+def test_escaped_stays_escaped_property(oracle):
+    """The CUDA kernel tests |z|^2 >= 4 only every 8th update (binary64) and replays the block on a
+    hit; that is exact iff a computed |z|^2 >= 4 is followed by 7 more that are >= 4 and finite, for
+    every c outside the thin annulus | |c|^2 - 4 | <= 2^-36 (those lanes are never deferred).  The
+    kernel header argues it from rounding bounds; this hammers it with the oracle's arithmetic."""
+    rng = np.random.default_rng(99)
+    n = 400_000
+    th = rng.uniform(0, 2 * np.pi, n)
+    sets = []
+    # (a) hugging the annulus from both sides, down to just outside the band
+    rad2 = 4.0 + rng.choice([-1, 1], n) * 2.0 ** rng.uniform(-36, -8, n)
+    rad = np.sqrt(rad2)
+    sets.append((rad * np.cos(th), rad * np.sin(th)))
+    # (b) around -2 on the real axis (the orbit hovers at z = 2) and the tips of the antennae
+    sets.append((-2.0 + rng.normal(0, 1e-6, n), rng.normal(0, 1e-6, n)))
+    sets.append((-2.0 + 2.0 ** rng.uniform(-50, -5, n) * rng.choice([-1, 1], n), 2.0 ** rng.uniform(-60, -5, n) * rng.choice([-1, 0, 1], n)))
+    # (c) the whole plane incl. the corners at |c| = 2.83, and the boundary of the set
+    sets.append((rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)))
+    t2 = rng.uniform(0, 2 * np.pi, n)
+    sets.append((0.5 * np.cos(t2) - 0.25 * np.cos(2 * t2) + rng.normal(0, 3e-3, n), 0.5 * np.sin(t2) - 0.25 * np.sin(2 * t2) + rng.normal(0, 3e-3, n)))
+    # (d) actual DataChunk grid points on the circle's neighbourhood (levels with 1.2 / 1.6 grid lines etc.)
+    for level in (1, 2, 4, 5, 10, 20):
+        g = np.linspace(-2, 2, level * 64 + 1)
+        rr, ii = np.meshgrid(g, g)
+        sets.append((rr.ravel(), ii.ravel()))
+    total = 0
+    for r, i in sets:
+        total += r.size
+        assert oracle.sticky_violations(r, i, 300, extra=7) == 0
+        # binary32 kernel: blocks of 16, `!(m < 4)` at the block end, band 2^-9
+        assert oracle.sticky_violations_f32(r, i, 300, extra=15) == 0
+    assert total > 2_000_000
+    # and closer to the binary32 band edge
+    rad2 = 4.0 + rng.choice([-1, 1], n) * 2.0 ** rng.uniform(-9, -3, n)
+    rad = np.sqrt(rad2)
+    assert oracle.sticky_violations_f32(rad * np.cos(th), rad * np.sin(th), 300, extra=15, band=2.0 ** -9) == 0
