@@ -94,6 +94,8 @@ SIGNATURES = {
     "mb_serialize_chunks": (_int, [_vp, _sz, _u32, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "mb_serialize_chunk_host": (_int, [_vp, _sz, _vp, _sz, C.POINTER(_u64)]),
     "mb_process_workload_serialized": (_int, [_u32, _u32, _u32, _u32, _u32, _vp, _sz, C.POINTER(_u64), C.POINTER(_i32)]),
+    "mb_host_alloc": (_int, [_sz, C.POINTER(_vp)]),
+    "mb_host_free": (_int, [_vp]),
     "mb_process_workload_u8": (_int, [_u32, _u32, _u32, _u32, _u32, _vp]),
     "mb_process_workload_counts": (_int, [_u32, _u32, _u32, _u32, _u32, _int, _vp]),
     "mb_wsq_create": (_int, [C.c_char_p, _u32, _u32, C.POINTER(_vp)]),
@@ -186,6 +188,67 @@ def measure_pipe_rate(dtype="f64", mode: int = 0, iters: int = 4096):
     rate, ms = C.c_double(), C.c_float()
     check(lib().mb_measure_pipe_rate(DTYPES[dtype], mode, iters, C.byref(rate), C.byref(ms)))
     return rate.value, ms.value
+
+
+class PinnedPool:
+    """Recycled page-locked host buffers handed out as numpy arrays.
+
+    `take(n)` returns a fresh-looking, writable uint8 array of n bytes that the caller owns like
+    any numpy array; when the array (and every view of it) is garbage-collected the page-locked
+    block goes back to the pool instead of being freed, so steady-state calls neither allocate nor
+    pin memory.  At most `keep` idle blocks per size are retained."""
+
+    def __init__(self, alloc=None, free=None, keep: int = 4):
+        self._alloc, self._free, self._keep = alloc, free, keep
+        self._idle = {}                          # nbytes -> [address, ...]
+        self._lock = threading.Lock()
+        self.allocated = 0
+
+    def _raw_alloc(self, n: int) -> int:
+        if self._alloc is not None:
+            return self._alloc(n)
+        p = _vp()
+        check(lib().mb_host_alloc(n, C.byref(p)))
+        return p.value
+
+    def _raw_free(self, addr: int) -> None:
+        if self._free is not None:
+            self._free(addr)
+        else:
+            lib().mb_host_free(_vp(addr))
+
+    def take(self, n: int):
+        import numpy as np
+        with self._lock:
+            idle = self._idle.get(n)
+            addr = idle.pop() if idle else None
+        if addr is None:
+            addr = self._raw_alloc(n)
+            self.allocated += 1
+        buf = (C.c_uint8 * n).from_address(addr)
+        buf._lease = _Lease(self, n, addr)       # dies with the last array/view over `buf`
+        return np.frombuffer(buf, dtype=np.uint8)
+
+    def _give_back(self, n: int, addr: int) -> None:
+        with self._lock:
+            idle = self._idle.setdefault(n, [])
+            if len(idle) < self._keep:
+                idle.append(addr)
+                return
+        self._raw_free(addr)
+
+
+class _Lease:
+    __slots__ = ("pool", "n", "addr")
+
+    def __init__(self, pool, n, addr):
+        self.pool, self.n, self.addr = pool, n, addr
+
+    def __del__(self):
+        try:
+            self.pool._give_back(self.n, self.addr)
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
 
 
 class TileQueue:

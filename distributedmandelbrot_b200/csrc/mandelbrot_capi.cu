@@ -418,6 +418,23 @@ int mb_classify_u8(const uint8_t *payload_dev, size_t n, uint32_t *flags_dev, vo
     return MB_OK;
 }
 
+int mb_host_alloc(size_t bytes, void **host_ptr)
+{
+    if (!host_ptr || bytes == 0) return fail(MB_ERR_INVALID, "bad argument");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    MB_CUDA(cudaHostAlloc(host_ptr, bytes, cudaHostAllocPortable));
+    return MB_OK;
+}
+
+int mb_host_free(void *host_ptr)
+{
+    if (!host_ptr) return MB_OK;
+    MB_CUDA(cudaFreeHost(host_ptr));
+    return MB_OK;
+}
+
 int mb_process_workload_u8(uint32_t level, uint32_t mrd, uint32_t index_real, uint32_t index_imag,
                            uint32_t definition, uint8_t *host_out)
 {

@@ -194,6 +194,11 @@ int mb_process_workload_serialized(uint32_t level, uint32_t mrd, uint32_t index_
                                    uint32_t index_imag, uint32_t definition, uint8_t *out_host,
                                    size_t out_capacity, uint64_t *out_len, int32_t *entry_type);
 
+/* Page-locked host memory for payload buffers (cudaHostAlloc / cudaFreeHost): a device->host copy
+ * into it runs at PCIe speed without the driver's staging pass that pageable memory needs. */
+int mb_host_alloc(size_t bytes, void **host_ptr);
+int mb_host_free(void *host_ptr);
+
 /* ---- one-call equivalents of process_workload (host buffers, synchronous) ------------- */
 
 /*

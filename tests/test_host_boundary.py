@@ -148,3 +148,33 @@ int main(void) {
     env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
+
+
+def test_pinned_pool_recycles_blocks(native):
+    """process_workload hands out page-locked payload buffers from a recycling pool; the pool logic
+    (no CUDA needed: malloc/free injected) must recycle a block only after every view of it died."""
+    import gc
+    libc = C.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes, libc.free.argtypes = C.c_void_p, [C.c_size_t], [C.c_void_p]
+    freed = []
+    pool = native.PinnedPool(alloc=lambda n: libc.malloc(n), free=lambda a: (freed.append(a), libc.free(a)), keep=2)
+    a = pool.take(1000)
+    assert a.dtype == np.uint8 and a.shape == (1000,) and a.flags.writeable and a.flags.c_contiguous
+    a[:] = 7
+    addr_a = a.ctypes.data
+    view = a[10:20]
+    del a
+    gc.collect()
+    b = pool.take(1000)                       # `view` still alive -> the block must NOT have been recycled
+    assert b.ctypes.data != addr_a and pool.allocated == 2
+    assert (view == 7).all()
+    del view
+    gc.collect()
+    c = pool.take(1000)                       # now it is
+    assert c.ctypes.data == addr_a and pool.allocated == 2
+    blocks = [pool.take(64) for _ in range(5)]
+    del blocks
+    gc.collect()
+    assert len(freed) == 3                    # keep = 2 idle blocks of a size, the rest is freed
+    del b, c
+    gc.collect()
