@@ -20,6 +20,10 @@ KEYS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__inst_executed_op_branch.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__thread_inst_executed_per_inst_executed.pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.avg.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_dmul_pred_on.avg.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.avg.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_ffma_pred_on.avg.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_fmul_pred_on.avg.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_fadd_pred_on.avg.per_cycle_elapsed",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
