@@ -20,6 +20,7 @@ path of its own and its numba-CUDA worker cannot run here).
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -33,11 +34,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gpixel-iterations/s"
 OPS_PER_PIXEL_ITERATION = 7          # FP64/FP32-pipe instructions the rounding sequence needs
-# Sum of useful pixel-iterations of the full frames as produced by the parity-tested single-GPU path
-# (tests/test_gpu_parity.py::test_cfg4_full_frame_properties; cfg5/cfg2/cfg3 recorded from the same build).
-# A multi-GPU run (work stealing + gather) must land on the same number: a fast frame that differs is wrong.
-EXPECTED_USEFUL = {"cfg4": 27_914_249_068_737, "cfg5": 6_306_807_763_045, "cfg2": 1_666_561_672, "cfg3": 104_413_119_766}
+ISSUED_PER_PIXEL_ITERATION = 6.125   # what the kernel issues in steady state: the magnitude add runs once per block of 8
 NOMINAL_FMA_TERA = {"f64": 148 * 64 * 1.965e9 / 1e12, "f32": 148 * 128 * 1.965e9 / 1e12}
+
+
+def expected_useful(name: str):
+    """Sum of useful pixel-iterations of a full BASELINE frame as the CPU ORACLE computes it
+    (tests/golden/fullsize_<cfg>.json, written by oracle/gen_fullsize_golden.py: every chunk rendered whole
+    with strict IEEE arithmetic; no number in there comes from a CUDA build).  The rendered frame --
+    one GPU or work-stolen across eight -- must land on it: a fast frame that differs is wrong."""
+    path = os.path.join(ROOT, "tests", "golden", f"fullsize_{name}.json")
+    try:
+        with open(path) as f:
+            doc = json.load(f)
+    except OSError:
+        return None
+    return doc["useful_total"] if doc.get("complete") else None
 
 
 def get_spec(name: str):
@@ -98,14 +110,31 @@ class ClockSampler:
 
 
 # ---- CPU baseline: the oracle on a bounded sample of the same frame -----------------------------
-def cpu_sample(spec, d: int, threads: int):
+def cpu_sample(spec, d: int, threads: int, simd: bool = False):
     """Render every chunk of the frame at reduced definition d with the oracle; (useful, seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     t0 = time.perf_counter()
     _counts, useful = oracle.render_frame(spec.level, spec.ir0, spec.ii0, spec.blocks, d, spec.mrd,
-                                          dtype=spec.dtype, threads=threads, want_counts=False)
+                                          dtype=spec.dtype, threads=threads, want_counts=False, simd=simd)
     return useful, time.perf_counter() - t0
+
+
+def cpu_baseline_simd(spec, d: int, budget_s: float = 8.0):
+    """Optional second CPU row: the same loop vectorised (oracle/mandel_oracle_simd.c: -O3,
+    AVX-512/AVX2 picked at load time, still no contraction, bit-identical counts) -- what a tuned CPU
+    port reaches on these cores.  Same sample window, definition scaled to the budget."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    threads = oracle.max_threads()
+    useful, sec = cpu_sample(spec, d, threads, simd=True)
+    if sec < budget_s / 4:
+        d = int(min(2048, d * min(4.0, (budget_s / max(sec, 1e-3)) ** 0.5 * 0.8)))
+        useful, sec = cpu_sample(spec, d, threads, simd=True)
+    return {"value": useful / sec / 1e9, "unit": METRIC, "cores": threads, "kind": "port, vectorised",
+            "vector_bits": oracle.simd_width(),
+            "sample": f"same frame, all {spec.n_chunks} chunks at d={d} ({useful:.4g} pixel-iterations in {sec:.1f} s); "
+                      f"gcc -O3 -ffp-contract=off, {oracle.simd_width()}-bit vectors, {threads} pthreads"}
 
 
 def cpu_quota() -> str:
@@ -175,11 +204,12 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"],
                     help="N > 1: nccl = one batched send/recv gather to rank 0; p2p = kernels store directly "
                          "into rank 0's frame buffer over NVLink peer memory (no gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shortcut", action="store_true", help="skip the separately reported periodicity-shortcut legs")
     args = ap.parse_args()
     spec = get_spec(args.workload)
     if args.impl == "reference":
@@ -190,7 +220,7 @@ def main() -> None:
     import torch.distributed as dist
     from distributedmandelbrot_b200 import _native as nat
     from distributedmandelbrot_b200 import worker
-    from distributedmandelbrot_b200.frame import FrameRenderer, probe_chunk_costs, queue_name, shared_frame_buffer
+    from distributedmandelbrot_b200.frame import FrameRenderer, InboxWorker, queue_name, shared_frame_buffer
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -202,6 +232,20 @@ def main() -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    barrier = dist.barrier if world > 1 else (lambda: None)
+
+    def allmax(x: float) -> float:
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_list(x: float):
+        if world == 1:
+            return [x]
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
 
     shared_out, close_shared = (None, None)
     if world > 1 and args.gather == "p2p":
@@ -216,14 +260,31 @@ def main() -> None:
         if rank != 0:
             queue = nat.TileQueue(qn)
 
-    def step():
+    diag = {"busy_ms": [], "gather_ms": [], "tail_ms": []}      # this rank, per timed step
+
+    def step(timed: bool = False):
         if world == 1:
             fr.render_all()                # every band in one launch
-        else:
-            fr.render_stolen(queue)        # work-stealing dispatch ...
-            if shared_out is None:
-                fr.gather_to_root()        # ... and the one collective: bands -> rank 0
-            # (p2p: the stores already landed in rank 0's buffer; the barrier + synchronize below close the step)
+            return
+        e_a = torch.cuda.Event(enable_timing=True)
+        e_b = torch.cuda.Event(enable_timing=True)
+        e_c = torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        fr.render_stolen(queue)            # work-stealing dispatch ...
+        e_b.record()
+        e_b.synchronize()                  # (the ownership exchange that follows blocks the host anyway)
+        t_done = time.monotonic()
+        if shared_out is None:
+            fr.gather_to_root()            # ... and the one collective: bands -> rank 0
+        # (p2p: the stores already landed in rank 0's buffer; the barrier + synchronize below close the step)
+        e_c.record()
+        if timed:
+            e_c.synchronize()
+            first, last = ctypes.c_double(), ctypes.c_double()
+            nat.check(nat.lib().mb_frame_last_stats(ctypes.byref(first), ctypes.byref(last)))
+            diag["busy_ms"].append(e_a.elapsed_time(e_b))                 # this GPU rendering its claims
+            diag["gather_ms"].append(e_b.elapsed_time(e_c))              # waiting for the others + the NCCL batch
+            diag["tail_ms"].append((t_done - last.value) * 1e3)           # last claim taken -> last kernel finished
 
     def rearm():
         if world > 1:
@@ -237,10 +298,14 @@ def main() -> None:
         step()
     torch.cuda.synchronize()
     useful = fr.useful_iterations() if rank == 0 else 0     # from the counts resident on rank 0
+    want = expected_useful(args.workload)
+    if rank == 0 and want is not None and useful != want:
+        raise SystemExit(f"PARITY GUARD: frame {args.workload} sums to {useful} useful pixel-iterations, the CPU oracle's "
+                         f"per-chunk digests (tests/golden/fullsize_{args.workload}.json) sum to {want} -- the rendered frame is wrong")
 
     sampler = ClockSampler(local)
     times = []
-    launches0 = fr.launches
+    launches0, steals0 = fr.launches, fr.steals
     if rank == 0:
         sampler.start()
     for _ in range(args.steps):
@@ -250,95 +315,119 @@ def main() -> None:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step()
+        step(timed=True)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)       # max over ranks
-        times.append(float(ms.item()))
+        times.append(allmax(e0.elapsed_time(e1)))            # max over ranks
     clocks = sampler.stop() if rank == 0 else None
     launches = torch.tensor([fr.launches - launches0], device=dev)
-    steals = torch.tensor([fr.steals], device=dev)
+    steals = torch.tensor([fr.steals - steals0], device=dev)
     if world > 1:
         dist.all_reduce(launches)
         dist.all_reduce(steals)
-    total_ms = sum(times)
-    ms_per_step = total_ms / args.steps
+    ms_per_step = sum(times) / args.steps
+    per_rank = None
+    if world > 1:
+        mean = lambda v: sum(v) / max(1, len(v))             # noqa: E731
+        per_rank = {k: gather_list(round(mean(v), 3)) for k, v in diag.items()}
+        per_rank["bands"] = gather_list(sum(c for _, c in fr.claimed))
 
-    # ---- e2e: the reference-facing worker API with HOST buffers (rank-local share of the chunks)
-    # chunks are handed out dynamically by a second work-stealing queue, the way a Distributer
-    # hands leases to whichever worker asks next
+    # ---- device-resident frame with the exact periodicity shortcut (separately reported, never `value`) ----
+    shortcut = None
+    if not args.no_shortcut:
+        fs = FrameRenderer(spec.scaled(shortcut=True), device=local, rank=rank, world=world, bands_per_claim=4, depth=6, out=fr.out)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def sc_step():
+            if world == 1:
+                fs.render_all()
+            else:
+                fs.render_stolen(queue)
+                if shared_out is None:
+                    fs.gather_to_root()
+
+        rearm()
+        nat.check(nat.lib().mb_set_executed_counter(counter.data_ptr()))
+        sc_step()                                              # warm-up pass; also counts the executed updates
+        torch.cuda.synchronize()
+        nat.check(nat.lib().mb_set_executed_counter(None))
+        executed = torch.tensor([int(counter.item())], device=dev)
+        if world > 1:
+            dist.all_reduce(executed)
+        sc_useful = fs.useful_iterations() if rank == 0 else 0
+        if rank == 0 and sc_useful != useful:
+            raise SystemExit(f"PARITY GUARD: the shortcut frame sums to {sc_useful}, the plain frame to {useful}")
+        sc_times = []
+        for _ in range(max(1, min(args.steps, 3))):
+            rearm()
+            barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sc_step()
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
+            sc_times.append(allmax(e0.elapsed_time(e1)))
+        shortcut = {"ms_per_step": statistics.median(sc_times), "executed_updates": int(executed.item())}
+        del fs
+
+    # ---- e2e: the reference-facing worker API with HOST buffers -------------------------------------
+    # N = 1: worker.process_workloads (whole chunks, pinned ring).  N > 1: frame.InboxWorker -- the same payloads,
+    # but chunks are cut into row bands, the bands go through the work-stealing queue and every rank copies its
+    # bands device->host straight into ONE shared pinned frame (no gather, no second copy).
     chunks = spec.chunk_indices()
     wl_all = [(spec.level, spec.mrd, ir, ii) for (ir, ii) in chunks]
-    e2e_s = None
+    e2e = e2e_sc = None
     if spec.dtype == "f64" and args.e2e_steps > 0:
-        cq = None
-        if world > 1:
-            cqn = queue_name() + "_c"
-            if rank == 0:
-                cq = nat.TileQueue(cqn, world, len(wl_all), create=True)
-            dist.barrier()
-            if rank != 0:
-                cq = nat.TileQueue(cqn)
-
-        order = list(range(len(wl_all)))
-
-        def source():
-            if cq is None:
-                yield from wl_all
-                return
-            while (g := cq.pop(rank, 1)) is not None:
-                for k in range(g[0], g[0] + g[1]):
-                    yield wl_all[order[k]]
-
-        worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None)   # warm the pinned ring
-        if world > 1:
-            probe_chunk_costs(spec, device=local)                                                   # ... and the probe's torch ops
-        total_s = 0.0
-        nbytes = 0
+        nbytes = [0]
 
         def consume(_w, payload):
-            nonlocal nbytes
-            nbytes += payload.nbytes
+            nbytes[0] += payload.nbytes
 
-        for _ in range(args.e2e_steps):
-            if world > 1:
+        def run_e2e(use_shortcut: bool):
+            secs = []
+            if world == 1:
+                worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None, shortcut=use_shortcut)   # warm the pinned ring
+                for _ in range(args.e2e_steps):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    worker.process_workloads(wl_all, definition=spec.definition, consume=consume, shortcut=use_shortcut)
+                    torch.cuda.synchronize()
+                    secs.append(time.perf_counter() - t0)
+                return secs, "worker.process_workloads (uint8 DataChunk payloads in pinned host memory, one per (level, mrd, ir, ii))"
+            iw = InboxWorker(wl_all, definition=spec.definition, band_rows=spec.band_rows, rank=rank, world=world, device=local,
+                             name=queue_name() + ("_s" if use_shortcut else "_e"), barrier=dist.barrier, shortcut=use_shortcut,
+                             bands_per_claim=4, depth=6)
+            iw.rearm()
+            iw.render()                                        # warm-up pass (staging buffers, page-locked mapping)
+            for _ in range(args.e2e_steps):
+                iw.rearm()
+                torch.cuda.synchronize()
                 dist.barrier()
-                if rank == 0:
-                    cq.reset(len(wl_all))
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            if world > 1:
-                # expensive chunks first (a 2 ms low-resolution probe, inside the timed region; every rank
-                # computes the same deterministic order)
-                costs = probe_chunk_costs(spec, device=local)
-                lpt = sorted(range(len(wl_all)), key=lambda k: -costs[k])
-                # the queue starts from a static contiguous split: deal the LPT order round-robin so that
-                # every rank's own range is "its share, expensive first" and steals take cheap chunks
-                order, n_all = [], len(wl_all)
-                for r in range(world):
-                    lo, hi = n_all * r // world, n_all * (r + 1) // world
-                    order += [lpt[j * world + r] for j in range(hi - lo) if j * world + r < n_all]
-                missing = [k for k in lpt if k not in set(order)]
-                order += missing
-            worker.process_workloads(source(), definition=spec.definition, consume=consume)
-            torch.cuda.synchronize()
-            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)       # max over ranks, per step
-            total_s += float(dt.item())
-        e2e_s = total_s / args.e2e_steps
-        if cq is not None:
-            dist.barrier()
-            cq.close()
+                t0 = time.perf_counter()
+                iw.render(consume=consume)                     # returns when this rank's bands are in host memory
+                dist.barrier()                                 # ... and the frame is complete when all ranks are here
+                secs.append(allmax(time.perf_counter() - t0))
+            holes = iw.missing()
+            iw.close()
+            if holes:
+                raise SystemExit(f"e2e: {len(holes)} bands never landed in the host frame")
+            return secs, ("frame.InboxWorker (band-granular work stealing; every rank copies its uint8 bands device->host into one "
+                          "shared page-locked frame; payloads byte-identical to process_workload)")
 
-    if rank == 0 and args.workload in EXPECTED_USEFUL and useful != EXPECTED_USEFUL[args.workload]:
-        raise SystemExit(f"PARITY GUARD: frame {args.workload} sums to {useful} useful pixel-iterations, "
-                         f"expected {EXPECTED_USEFUL[args.workload]} -- the rendered frame is wrong")
+        secs, api = run_e2e(False)
+        e2e = {"value": useful / statistics.median(secs) / 1e9 if rank == 0 else 0.0, "unit": METRIC,
+               "h2d_bytes_per_step": 88 * (spec.n_chunks if world == 1 else spec.n_bands), "d2h_bytes_per_step": spec.pixels,
+               "api": api, "steps": args.e2e_steps, "s_per_step": statistics.median(secs), "s_min": min(secs), "s_max": max(secs),
+               "statistic": "median over steps of the max over ranks"}
+        if not args.no_shortcut:
+            secs, _ = run_e2e(True)
+            e2e_sc = {"value": useful / statistics.median(secs) / 1e9 if rank == 0 else 0.0, "unit": METRIC, "steps": args.e2e_steps,
+                      "s_per_step": statistics.median(secs), "s_min": min(secs), "s_max": max(secs)}
+
     if rank == 0:
         value = useful / (ms_per_step * 1e-3) / 1e9
         peak_fma, _ = nat.measure_pipe_rate(spec.dtype, 0, 16384)        # tera FMA-pipe lane-ops/s, live
@@ -346,16 +435,16 @@ def main() -> None:
         # dominant kernel = escape_tiles_kernel; at N = 1 a step IS one launch of it
         achieved_tflops = ops_per_s * 2 / 1e12 * (1.0 if world == 1 else 1.0 / world)
         peak_tflops = peak_fma * 2
-        traffic = None
+        prof = {}
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(args.workload)
+                prof = json.load(open(tpath))
             except Exception:  # noqa: BLE001
-                traffic = None
+                prof = {}
         out = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_min": min(times), "ms_max": max(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": spec.dtype,
             "data": "synthetic (pure function of chunk indices; no RNG, no seeds)",
             "config": {"workload": spec.name, "level": spec.level, "blocks": spec.blocks,
@@ -367,27 +456,45 @@ def main() -> None:
                                                                                       else "kernel stores directly into rank 0's buffer over NVLink peer memory"),
                        "l2": f"kernel reads only 88-byte descriptors; output {spec.pixels * 4 / 2**30:.1f} GiB int32 per step >> 126 MB L2 (no L2 flush needed)",
                        "steals": int(steals.item()),
-                       "parity_guard": "frame sum equals the parity-tested single-GPU value" if args.workload in EXPECTED_USEFUL else "none for this workload"},
+                       "parity_guard": ("frame sum equals the CPU oracle's per-chunk digests (tests/golden/fullsize_*.json)" if want is not None
+                                        else "none for this workload")},
             "clocks": clocks,
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "fp64_pipe" if spec.dtype == "f64" else "fp32_pipe",
                          "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak_tflops,
+                         "frac_issued": achieved_tflops / peak_tflops * ISSUED_PER_PIXEL_ITERATION / OPS_PER_PIXEL_ITERATION,
                          "per_gpu": world > 1,
-                         "convention": f"{OPS_PER_PIXEL_ITERATION} pipe instructions per pixel-iteration, each counted as one FMA slot = 2 FLOP",
-                         "peak_source": "measured live: mb_measure_fma_peak (independent FMA chains on all SMs) on this GPU",
+                         "convention": f"frac counts the {OPS_PER_PIXEL_ITERATION} pipe instructions the reference's rounding sequence defines per "
+                                       f"pixel-iteration (each one FMA slot = 2 FLOP) and may exceed 1; frac_issued counts the "
+                                       f"{ISSUED_PER_PIXEL_ITERATION} the kernel issues (magnitude add once per block of 8)",
+                         "ncu_pipe_busy": prof.get("fp64_pipe_busy_frac" if spec.dtype == "f64" else "fp32_issue_busy_frac"),
+                         "ncu_source": prof.get("pipe_busy_source"),
+                         "peak_source": "builder-measured, live in this run: mb_measure_fma_peak (independent FMA chains on all SMs of this GPU); "
+                                        "MEASURED_PEAKS.json has no FP64/FP32 FMA entry",
                          "nominal_peak": NOMINAL_FMA_TERA[spec.dtype] * 2,
-                         "algorithmic_bytes_per_launch": spec.pixels * 4, "traffic": traffic},
+                         "frac_of_nominal": achieved_tflops / (NOMINAL_FMA_TERA[spec.dtype] * 2),
+                         "algorithmic_bytes_per_launch": spec.pixels * 4, "traffic": prof.get(args.workload)},
+            "e2e": e2e,
         }
-        if spec.dtype == "f64" and args.e2e_steps > 0:
-            out["e2e"] = {"value": useful / e2e_s / 1e9, "unit": METRIC,
-                          "h2d_bytes_per_step": 88 * spec.n_chunks, "d2h_bytes_per_step": spec.pixels,
-                          "api": "worker.process_workloads (uint8 DataChunk payloads in host memory, one per (level, mrd, ir, ii))",
-                          "steps": args.e2e_steps, "s_per_step": e2e_s}
-        else:
-            out["e2e"] = None
+        if per_rank is not None:
+            # which of these is large names the limiter: busy_ms spread = imbalance the queue did not fix,
+            # tail_ms = size of the last claims, gather_ms (on the fastest rank) = waiting + the collective
+            out["per_rank"] = per_rank
+        if shortcut is not None:
+            out["value_shortcut"] = {"value": useful / (shortcut["ms_per_step"] * 1e-3) / 1e9, "unit": METRIC,
+                                     "ms_per_step": shortcut["ms_per_step"], "executed_updates": shortcut["executed_updates"],
+                                     "executed_fraction": shortcut["executed_updates"] / useful,
+                                     "note": "MB_TILE_PERIOD_SHORTCUT: bit-identical counts (parity suite runs with it on), credited work "
+                                             "unchanged, executed work reduced; never used for `value` or `roofline`"}
+        if e2e_sc is not None:
+            out["e2e_shortcut"] = e2e_sc
         if not args.no_cpu_baseline and world == 1:      # timed on rank 0 at N = 1 only
-            out["cpu_baseline"], _d = cpu_baseline(spec)
+            out["cpu_baseline"], d_used = cpu_baseline(spec)
+            try:
+                out["cpu_baseline_simd"] = cpu_baseline_simd(spec, d_used)
+            except Exception as exc:  # noqa: BLE001 -- informational row only
+                out["cpu_baseline_simd"] = {"error": str(exc)}
         print(json.dumps(out), flush=True)
 
     if queue is not None:

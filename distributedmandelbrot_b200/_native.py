@@ -18,6 +18,7 @@ MB_ERR_INVALID, MB_ERR_CUDA, MB_ERR_NOMEM, MB_ERR_STATE, MB_ERR_SYS = -1, -2, -3
 DTYPE_F64, DTYPE_F32 = 0, 1
 DTYPES = {"f64": DTYPE_F64, "f32": DTYPE_F32, DTYPE_F64: DTYPE_F64, DTYPE_F32: DTYPE_F32}
 CHUNK_DEFINITION = 4096   # DataChunk.dataChunkRange (DataChunk.cs:20) ; .py:80
+TILE_PERIOD_SHORTCUT = 1  # mb_tile.flags bit 0: exact orbit-periodicity shortcut (bit-identical counts)
 
 
 class NativeError(RuntimeError):
@@ -68,7 +69,7 @@ class ChunkInfo(C.Structure):
 assert C.sizeof(ChunkInfo) == 32
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 
 # name -> (restype, argtypes); every symbol include/mandelbrot_b200.h declares
 _u32, _i32, _u64, _sz, _vp, _int = C.c_uint32, C.c_int32, C.c_uint64, C.c_size_t, C.c_void_p, C.c_int
@@ -80,6 +81,27 @@ SIGNATURES = {
     "mb_abi_version": (_int, []),
     "mb_device_count": (_int, []),
     "mb_sm_count": (_int, []),
+    "mb_set_period_shortcut": (_int, [_int]),
+    "mb_set_executed_counter": (_int, [_vp]),
+    "mb_frame_last_stats": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mb_hostframe_create": (_int, [C.c_char_p, _u64, _u32, _u32, C.POINTER(_vp)]),
+    "mb_hostframe_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
+    "mb_hostframe_data": (_vp, [_vp]),
+    "mb_hostframe_bytes": (_u64, [_vp]),
+    "mb_hostframe_units": (_u32, [_vp]),
+    "mb_hostframe_groups": (_u32, [_vp]),
+    "mb_hostframe_reset": (_int, [_vp]),
+    "mb_hostframe_pin": (_int, [_vp]),
+    "mb_hostframe_unpin": (_int, [_vp]),
+    "mb_hostframe_mark_done": (_int, [_vp, _u32, _u32, C.POINTER(_u32), _u32, C.POINTER(_u32)]),
+    "mb_hostframe_group_left": (C.c_int64, [_vp, _u32]),
+    "mb_hostframe_missing": (_int, [_vp, C.POINTER(_u32), _u32, C.POINTER(_u32)]),
+    "mb_hostframe_close": (_int, [_vp]),
+    "mb_hostframe_unlink": (_int, [C.c_char_p]),
+    "mb_frame_render_u8_host": (_int, [_vp, _u32, _u32, _PT, _u32, _u32, _u32, _vp, _int, C.POINTER(_u32), _u32,
+                                       C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), _u32, C.POINTER(_u32)]),
+    "mb_frame_render_u8_host_units": (_int, [C.POINTER(_u32), _u32, _PT, _u32, _u32, _vp, _int, C.POINTER(_u32), _u32,
+                                             C.POINTER(_u32)]),
     "mb_chunk_geometry": (_int, [_u32, _u32, _u32, _u32, _u32, _PT]),
     "mb_tile_coord": (C.c_double, [_PT, _int, _u32]),
     "mb_render_counts": (_int, [_PT, _u32, _vp, _int, _vp]),
@@ -127,6 +149,8 @@ def lib() -> C.CDLL:
         if _lib is None:
             if not os.path.exists(_build.SO):
                 _build.build()
+            elif _build.stale() and _build.have_nvcc():
+                _build.build()               # edited csrc/ since the last build: never load a stale binary
             L = C.CDLL(_build.SO)
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(L, name)   # AttributeError here = header/library mismatch: fail loudly
@@ -163,15 +187,24 @@ def ensure_init(device: int | None = None) -> int:
     return device
 
 
+def set_period_shortcut(enabled: bool) -> bool:
+    """Switch the one-call entry points (process_workload & co) of THIS thread to the exact
+    orbit-periodicity shortcut; returns the previous setting.  Counts are identical either way."""
+    return bool(lib().mb_set_period_shortcut(1 if enabled else 0))
+
+
 def chunk_geometry(level: int, index_real: int, index_imag: int, definition: int = CHUNK_DEFINITION,
-                   mrd: int = 0) -> Tile:
-    """Whole-chunk tile descriptor (.py:75-78 + linspace parameters of .py:24-32).  Host only."""
+                   mrd: int = 0, shortcut: bool = False) -> Tile:
+    """Whole-chunk tile descriptor (.py:75-78 + linspace parameters of .py:24-32).  Host only.
+    shortcut=True sets MB_TILE_PERIOD_SHORTCUT on the tile (and on every sub-tile cut from it)."""
     for name, v in (("level", level), ("index_real", index_real), ("index_imag", index_imag),
                     ("definition", definition), ("mrd", mrd)):
         if not (0 <= int(v) <= 0xFFFFFFFF):
             raise InvalidArgument(MB_ERR_INVALID, f"{name}={v} is not a uint32")
     t = Tile()
     check(lib().mb_chunk_geometry(int(level), int(index_real), int(index_imag), int(definition), int(mrd), C.byref(t)))
+    if shortcut:
+        t.flags = TILE_PERIOD_SHORTCUT
     return t
 
 
@@ -201,7 +234,7 @@ class PinnedPool:
     def __init__(self, alloc=None, free=None, keep: int = 4):
         self._alloc, self._free, self._keep = alloc, free, keep
         self._idle = {}                          # nbytes -> [address, ...]
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()           # re-entrant: _give_back may run from __del__ inside take() (cyclic GC)
         self.allocated = 0
 
     def _raw_alloc(self, n: int) -> int:
@@ -224,7 +257,8 @@ class PinnedPool:
             addr = idle.pop() if idle else None
         if addr is None:
             addr = self._raw_alloc(n)
-            self.allocated += 1
+            with self._lock:
+                self.allocated += 1
         buf = (C.c_uint8 * n).from_address(addr)
         buf._lease = _Lease(self, n, addr)       # dies with the last array/view over `buf`
         return np.frombuffer(buf, dtype=np.uint8)
@@ -291,3 +325,69 @@ class TileQueue:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class HostFrame:
+    """mb_hostframe: the uint8 payloads of one frame in POSIX shared memory, page-locked by every GPU
+    process of the box, with per-band / per-chunk completion counters (csrc/host_frame.cpp)."""
+
+    def __init__(self, name: str, payload_bytes: int | None = None, n_units: int | None = None,
+                 units_per_group: int | None = None, create: bool = False):
+        self.name = name.encode()
+        self._h = _vp()
+        self._owner = create
+        self._pinned = False
+        if create:
+            check(lib().mb_hostframe_create(self.name, payload_bytes, n_units, units_per_group, C.byref(self._h)))
+        else:
+            check(lib().mb_hostframe_open(self.name, C.byref(self._h)))
+        self.nbytes = int(lib().mb_hostframe_bytes(self._h))
+        self.n_units = int(lib().mb_hostframe_units(self._h))
+        self.n_groups = int(lib().mb_hostframe_groups(self._h))
+        self._array = None
+
+    @property
+    def array(self):
+        """numpy uint8 view of the payload area (valid until close())."""
+        import numpy as np
+        if self._array is None:
+            ptr = lib().mb_hostframe_data(self._h)
+            self._array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(ptr))
+        return self._array
+
+    def pin(self) -> None:
+        check(lib().mb_hostframe_pin(self._h))
+        self._pinned = True
+
+    def reset(self) -> None:
+        check(lib().mb_hostframe_reset(self._h))
+
+    def mark_done(self, first: int, count: int = 1):
+        """Publish units [first, first+count); returns the groups (chunks) this completed."""
+        cap = count
+        buf, n = (_u32 * cap)(), _u32(0)
+        check(lib().mb_hostframe_mark_done(self._h, first, count, buf, cap, C.byref(n)))
+        return [buf[k] for k in range(min(n.value, cap))]
+
+    def group_left(self, group: int) -> int:
+        return int(check(lib().mb_hostframe_group_left(self._h, group)))
+
+    def missing(self):
+        n = _u32()
+        check(lib().mb_hostframe_missing(self._h, None, 0, C.byref(n)))
+        if n.value == 0:
+            return []
+        buf = (_u32 * n.value)()
+        check(lib().mb_hostframe_missing(self._h, buf, n.value, C.byref(n)))
+        return list(buf[:n.value])
+
+    def close(self) -> None:
+        if self._h:
+            self._array = None
+            if self._pinned:
+                lib().mb_hostframe_unpin(self._h)
+                self._pinned = False
+            lib().mb_hostframe_close(self._h)
+            self._h = _vp()
+            if self._owner:
+                lib().mb_hostframe_unlink(self.name)

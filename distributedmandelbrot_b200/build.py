@@ -10,7 +10,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libmandelbrot_b200.so")
-SOURCES = ["mandelbrot_capi.cu", "tile_wsq.cpp"]
+STAMP = SO + ".srchash"
+SOURCES = ["mandelbrot_capi.cu", "tile_wsq.cpp", "host_frame.cpp"]
 HEADERS = ["escape_kernels.cuh", "chunk_codec.cuh", os.path.join("..", "..", "include", "mandelbrot_b200.h")]
 
 NVCC_FLAGS = [
@@ -30,19 +31,42 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def have_nvcc() -> bool:
+    try:
+        nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def source_hash() -> str:
+    """sha256 over the sources, headers and flags the library is built from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def stale() -> bool:
+    """True when the .so was not built from the sources as they are now.  Content hash in a sidecar
+    file, not mtimes: the tree is copied to the GPU box and copies do not keep file times."""
     if not os.path.exists(SO):
         return True
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or stale()):
         return SO
+    tmp = f"{SO}.{os.getpid()}.tmp"          # several ranks may get here at once: build aside, rename atomically
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lrt"]
+          ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lrt"]
     env = dict(os.environ)
     env.pop("CC", None)   # $CC in this image points at a wrapper gcc nvcc must not pick up
     env.pop("CXX", None)
@@ -50,7 +74,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    os.replace(tmp, SO)
+    with open(STAMP + ".tmp", "w") as f:
+        f.write(source_hash() + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return SO
 
 

@@ -47,6 +47,8 @@ template <> struct Ops<double> {
     static __device__ __forceinline__ double coord(double v) { return v; }
     static __device__ __forceinline__ bool ordinary(double cr, double ci) { return fabs(cr) <= 4.0 && fabs(ci) <= 4.0; }
     static __device__ __forceinline__ bool ge4(double m) { return m >= 4.0; }     // IEEE compare: false for NaN
+    // bit equality on the ALU pipe (integer compares; an FP compare would cost an FP64-pipe slot)
+    static __device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 };
 
 template <> struct Ops<float> {
@@ -59,6 +61,7 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ float coord(double v) { return __double2float_rn(v); }
     static __device__ __forceinline__ bool ordinary(float cr, float ci) { return fabsf(cr) <= 4.0f && fabsf(ci) <= 4.0f; }
     static __device__ __forceinline__ bool ge4(float m) { return m >= 4.0f; }
+    static __device__ __forceinline__ bool same_bits(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
 };
 
 // ---- deferred escape test ---------------------------------------------------------------------
@@ -114,8 +117,24 @@ __device__ __forceinline__ void update(Real &x, Real &y, Real &xx, Real &yy, Rea
 // structure is warp-uniform; after every block one warp vote lets the whole warp leave as soon as
 // every lane has escaped or hit mrd.  HEAD = number of leading updates that are always tested
 // (pixels that escape early -- most pixels outside the set -- never pay for a replay).
-template <typename Real, int HEAD>
-__device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool active)
+//
+// PERIOD (opt-in, mb_tile.flags & MB_TILE_PERIOD_SHORTCUT): exact orbit-periodicity shortcut.
+// The floating-point orbit is a deterministic map on a finite set of (x, y) bit patterns, so an
+// orbit that does not escape ends in an exact cycle -- for most pixels inside the set within a few
+// hundred or thousand updates (an attracting cycle contracts the orbit onto it until the rounding
+// grid stops it).  If the state at the end of a trip (two blocks, 2K updates) is BIT-EQUAL to a
+// state saved at an earlier trip end, then z_{m+k} == z_{n+k} for every k: the orbit repeats the
+// segment (m, n] forever.  Every update of the head was tested and every block up to n ended with
+// an untripped test -- and an untripped block contains no escape (property (P), DESIGN.md
+// Appendix A) -- so no m_j, j <= n, reached 4, hence none ever will: the reference loop
+// (.py:47-68) runs to mrd-1 and returns 0, which is what the lane reports, without iterating.
+// Brent's scheme: the saved state is replaced whenever the update count n reaches a power of two
+// (saved at n = 2^k, compared at n = 2^k + 2K*j), so any cycle of period p is found once
+// 2^k >= p * 2K / gcd(p, 2K) and the orbit has landed on it.  Cost: two 64-bit integer compares
+// per 2K updates on the ALU pipe (not DSETP: the FP64 pipe stays clean), 4 registers.  The counts
+// are identical with the flag on or off (tests/test_gpu_parity.py::test_period_shortcut_*).
+template <typename Real, int HEAD, bool PERIOD = false>
+__device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool active, int *executed = nullptr)
 {
     using O = Ops<Real>;
     constexpr int K = Defer<Real>::K;
@@ -127,6 +146,7 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
     int left = mrd - 1;                        // updates still allowed: n = 1 .. mrd-1 (.py:47)
     int n = 0;                                 // updates performed
     int result = 0;                            // 0 = never escaped (.py:68)
+    Real sx = cr, sy = ci;                     // PERIOD: saved state (z0 = c is a legitimate first sample)
     bool done = !active || left <= 0;
     if (!done && !O::ordinary(cr, ci)) {
         // Coordinates outside [-4, 4]^2 (only reachable through calc_mb_value or a hand-made tile:
@@ -163,7 +183,7 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
                 // every exit leaves at the start of the block that tripped.  Two blocks per trip in
                 // explicit SSA form: block A reads (x, y) without overwriting them, block B reads
                 // A's results, and only the cold exit of B copies A's start into (x, y).
-                bool tripped = false;
+                bool tripped = false, periodic = false;
                 {
                     Real ax, ay, axx, ayy, bx, by, bxx, byy;
                     while (left >= 2 * K) {
@@ -180,8 +200,12 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
                         x = bx; y = by; xx = bxx; yy = byy;
                         n += K;
                         left -= K;
+                        if constexpr (PERIOD) {
+                            if (O::same_bits(x, sx) && O::same_bits(y, sy)) { periodic = true; break; }
+                            if ((n & (n - 1)) == 0) { sx = x; sy = y; }
+                        }
                     }
-                    if (!tripped && left >= K) {
+                    if (!tripped && !periodic && left >= K) {
                         ax = x; ay = y; axx = xx; ayy = yy;
 #pragma unroll
                         for (int j = 0; j < K; ++j) update<Real>(ax, ay, axx, ayy, cr, ci);
@@ -198,7 +222,7 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
                     }
                     done = true;
                 }
-                done = done || (left == 0);
+                done = done || periodic || (left == 0);      // periodic: never escapes, result stays 0
             } else {
                 // head of the orbit (and `risky` lanes): test after every update
 #pragma unroll
@@ -213,6 +237,8 @@ __device__ __forceinline__ int escape_count(Real cr, Real ci, int mrd, bool acti
         }
         if (__all_sync(kFull, done)) break;    // warp-vote early-out
     }
+    // updates this lane executed (replays not counted): the escape index, or where it stopped
+    if constexpr (PERIOD) { if (executed) *executed = !active ? 0 : (result ? result : n); }
     return result;
 }
 
@@ -237,12 +263,13 @@ struct TileArgs {
     const mb_tile *dev;                 // used when n_inline == 0
     uint32_t n_inline;
     uint32_t pad;
+    unsigned long long *executed;       // PERIOD only, may be NULL: += updates actually executed
     mb_tile inl[kInlineTiles];
 };
 
 // CTA = WX x WY warps; each warp an 8x4 patch.  grid.x = CTAs per tile (row-major over the
 // tile), grid.y = tile index.  OutT = int32_t (counts) or uint8_t (fused .py:96-98 epilogue).
-template <typename Real, typename OutT, int HEAD, int WX, int WY, int MIN_CTAS>
+template <typename Real, typename OutT, int HEAD, int WX, int WY, int MIN_CTAS, bool PERIOD = false>
 __global__ void __launch_bounds__(WX * WY * 32, MIN_CTAS)
 escape_tiles_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ out)
 {
@@ -270,7 +297,15 @@ escape_tiles_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ ou
     const double ci64 = linspace_at(s_tile.y0 + py, d1, s_tile.start_i, s_tile.step_i, s_tile.stop_i);
     const uint32_t mrd = s_tile.mrd;
 
-    const int res = escape_count<Real, HEAD>(Ops<Real>::coord(cr64), Ops<Real>::coord(ci64), (int)mrd, active);
+    int exec_n = 0;
+    const int res = escape_count<Real, HEAD, PERIOD>(Ops<Real>::coord(cr64), Ops<Real>::coord(ci64), (int)mrd, active, &exec_n);
+    if constexpr (PERIOD) {
+        if (args.executed) {                   // diagnostic: executed vs required updates (bench.py e2e_shortcut)
+            unsigned long long tot = (unsigned long long)exec_n;
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(kFull, tot, o);
+            if (lane == 0 && tot) atomicAdd(args.executed, tot);
+        }
+    }
 
     const size_t row_off = s_tile.out_offset + (size_t)py * s_tile.out_pitch;
     if constexpr (sizeof(OutT) == 4) {

@@ -7,11 +7,14 @@
 // every compute entry point either launches a CUDA kernel or fails.
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "chunk_codec.cuh"
 #include "escape_kernels.cuh"
@@ -20,6 +23,16 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_device = -1;
+thread_local uint32_t g_tile_flags = 0;     // mb_set_period_shortcut: flags of the one-call entry points' tiles
+thread_local unsigned long long *g_executed = nullptr;   // mb_set_executed_counter (shortcut launches only)
+thread_local double g_first_claim = 0.0, g_last_claim = 0.0;   // mb_frame_last_stats
+
+double now_monotonic()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 #ifdef MB_TUNING_VARIANTS
 int g_variant = 0;
 #endif
@@ -51,7 +64,25 @@ struct DeviceCtx {
     cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};   // concurrent launch lanes of the dispatch loop
     void *scratch = nullptr;            // device output buffer of the host-buffer entry points
     size_t scratch_bytes = 0;
+    void *stage[16] = {};               // per-slot device staging of mb_frame_render_u8_host
+    size_t stage_bytes[16] = {};
     std::mutex mu;
+};
+
+// events that are destroyed on every exit path
+struct EventSet {
+    cudaEvent_t ev[20];
+    uint32_t n = 0;
+    int add(uint32_t count)
+    {
+        for (uint32_t k = 0; k < count && n < 20; ++k) {
+            cudaError_t e = cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming);
+            if (e != cudaSuccess) return (int)e;
+            ++n;
+        }
+        return 0;
+    }
+    ~EventSet() { for (uint32_t k = 0; k < n; ++k) cudaEventDestroy(ev[k]); }
 };
 DeviceCtx g_ctx[kMaxDevices];
 
@@ -89,7 +120,8 @@ int check_tiles(const mb_tile *tiles, uint32_t n_tiles, uint32_t *max_w, uint32_
             return fail(MB_ERR_INVALID, "tile %u: rectangle exceeds the chunk grid", k);
         if (t.mrd > 0x7fffffffu) return fail(MB_ERR_INVALID, "tile %u: mrd exceeds int32 (.py:39)", k);
         if (t.out_pitch < t.w) return fail(MB_ERR_INVALID, "tile %u: out_pitch < w", k);
-        if (t.flags != 0) return fail(MB_ERR_INVALID, "tile %u: flags must be 0", k);
+        if (t.flags & ~(uint32_t)MB_TILE_PERIOD_SHORTCUT) return fail(MB_ERR_INVALID, "tile %u: unknown flag bits 0x%x", k, t.flags);
+        if (t.flags != tiles[0].flags) return fail(MB_ERR_INVALID, "tile %u: every tile of one launch must carry the same flags", k);
         mw = t.w > mw ? t.w : mw;
         mh = t.h > mh ? t.h : mh;
     }
@@ -123,6 +155,7 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
     // ones in a stream-ordered device allocation (the pool keeps its memory, see mb_init).
     mbk::TileArgs args;
     std::memset(&args, 0, sizeof(args));
+    args.executed = g_executed;          // only read by the shortcut instantiations
     mb_tile *tiles_dev = nullptr;
     if (n_tiles <= (uint32_t)mbk::kInlineTiles) {
         args.n_inline = n_tiles;
@@ -172,10 +205,14 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
             const uint32_t cnt = (n_tiles - first < kMaxGridY) ? n_tiles - first : kMaxGridY;
             const dim3 grid(ctas_per_tile, cnt, 1), block(kWX * kWY * 32, 1, 1);
             args.dev = tiles_dev ? tiles_dev + first : nullptr;
-            if (dtype == MB_DTYPE_F64)
-                mbk::escape_tiles_kernel<double, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
-            else
-                mbk::escape_tiles_kernel<float, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
+            const bool period = (tiles[0].flags & MB_TILE_PERIOD_SHORTCUT) != 0;   // exact shortcut, opt-in
+            if (dtype == MB_DTYPE_F64) {
+                if (period) mbk::escape_tiles_kernel<double, OutT, kHead, kWX, kWY, kMinCtas, true><<<grid, block, 0, st>>>(args, out_dev);
+                else mbk::escape_tiles_kernel<double, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
+            } else {
+                if (period) mbk::escape_tiles_kernel<float, OutT, kHead, kWX, kWY, kMinCtas, true><<<grid, block, 0, st>>>(args, out_dev);
+                else mbk::escape_tiles_kernel<float, OutT, kHead, kWX, kWY, kMinCtas><<<grid, block, 0, st>>>(args, out_dev);
+            }
             err = cudaGetLastError();
         }
         if (err != cudaSuccess) rc = fail(MB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
@@ -259,6 +296,7 @@ void mb_shutdown(void)
         if (!c.ready) continue;
         cudaSetDevice(d);
         if (c.scratch) cudaFree(c.scratch);
+        for (int k = 0; k < 16; ++k) { if (c.stage[k]) cudaFree(c.stage[k]); c.stage[k] = nullptr; c.stage_bytes[k] = 0; }
         if (c.stream) cudaStreamDestroy(c.stream);
         for (auto &ln : c.lanes) { if (ln) cudaStreamDestroy(ln); ln = nullptr; }
         c.scratch = nullptr;
@@ -267,6 +305,19 @@ void mb_shutdown(void)
         c.ready = false;
     }
     g_device = -1;
+}
+
+int mb_set_period_shortcut(int enabled)
+{
+    const int was = (g_tile_flags & MB_TILE_PERIOD_SHORTCUT) ? 1 : 0;
+    g_tile_flags = enabled ? (g_tile_flags | MB_TILE_PERIOD_SHORTCUT) : (g_tile_flags & ~(uint32_t)MB_TILE_PERIOD_SHORTCUT);
+    return was;
+}
+
+int mb_set_executed_counter(uint64_t *counter_dev)
+{
+    g_executed = reinterpret_cast<unsigned long long *>(counter_dev);
+    return MB_OK;
 }
 
 int mb_sm_count(void)
@@ -442,6 +493,7 @@ int mb_process_workload_u8(uint32_t level, uint32_t mrd, uint32_t index_real, ui
     mb_tile t;
     int rc = mb_chunk_geometry(level, index_real, index_imag, definition, mrd, &t);
     if (rc) return rc;
+    t.flags = g_tile_flags;
     DeviceCtx *c = nullptr;
     if ((rc = current_ctx(&c))) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -460,6 +512,7 @@ int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real
     mb_tile t;
     int rc = mb_chunk_geometry(level, index_real, index_imag, definition, mrd, &t);
     if (rc) return rc;
+    t.flags = g_tile_flags;
     DeviceCtx *c = nullptr;
     if ((rc = current_ctx(&c))) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -533,6 +586,7 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
     DeviceCtx *c = nullptr;
     int rc = current_ctx(&c);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);          // the lanes belong to the device context: one dispatch loop at a time
     cudaStream_t st = (cudaStream_t)stream;
     // Claims go round-robin onto kLanes internal streams so that the drain of one launch (a few
     // long-running CTAs at the set boundary) overlaps the head of the next; in one stream every
@@ -540,14 +594,16 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
     // The lanes start after everything already enqueued on `stream`, and `stream` waits for the
     // lanes before this function returns, so callers keep plain stream semantics.
     constexpr uint32_t kLanes = 4;
-    cudaEvent_t ring[16], fence;
-    MB_CUDA(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
-    MB_CUDA(cudaEventRecord(fence, st));
-    for (uint32_t k = 0; k < kLanes; ++k) MB_CUDA(cudaStreamWaitEvent(c->lanes[k], fence, 0));
-    for (uint32_t k = 0; k < depth; ++k) MB_CUDA(cudaEventCreateWithFlags(&ring[k], cudaEventDisableTiming));
+    EventSet evs;                                    // [0] = fence, [1 .. depth] = ring; destroyed on every exit path
+    if (evs.add(1 + depth)) return fail(MB_ERR_CUDA, "cudaEventCreate failed");
+    cudaEvent_t fence = evs.ev[0], *ring = &evs.ev[1];
     uint32_t claims = 0, stolen_total = 0;
     int result = MB_OK;
-    for (;;) {
+    cudaError_t e = cudaEventRecord(fence, st);
+    for (uint32_t k = 0; k < kLanes && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(c->lanes[k], fence, 0);
+    if (e != cudaSuccess) result = fail(MB_ERR_CUDA, "lane fence: %s", cudaGetErrorString(e));
+    g_first_claim = g_last_claim = now_monotonic();
+    while (result == MB_OK) {
         const int64_t remaining = mb_wsq_remaining(q);
         uint32_t want = (uint32_t)(remaining / ((int64_t)n_ranks * 8));
         if (want > bands_per_claim) want = bands_per_claim;
@@ -556,29 +612,217 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
         const int pr = mb_wsq_pop(q, rank, want, &first, &got, &stolen);
         if (pr < 0) { result = pr; break; }
         if (pr == 0) break;
+        if (claims == 0) g_first_claim = now_monotonic();
+        g_last_claim = now_monotonic();
         if ((uint64_t)first + got > n_tiles) { result = fail(MB_ERR_STATE, "queue handed out tile %u of %u", first + got - 1, n_tiles); break; }
         if (claims >= max_claims) { result = fail(MB_ERR_INVALID, "claimed[] too small (%u claims)", max_claims); break; }
         if (claims >= depth) {                              // at most `depth` launches in flight
-            cudaError_t e = cudaEventSynchronize(ring[claims % depth]);
+            e = cudaEventSynchronize(ring[claims % depth]);
             if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e)); break; }
         }
         cudaStream_t lane = c->lanes[claims % kLanes];
         if ((result = mb_render_counts(tiles + first, got, out_dev, dtype, lane))) break;
-        cudaError_t e = cudaEventRecord(ring[claims % depth], lane);
+        e = cudaEventRecord(ring[claims % depth], lane);
         if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e)); break; }
         claimed[2 * claims] = first;
         claimed[2 * claims + 1] = got;
         ++claims;
         stolen_total += stolen;
     }
-    for (uint32_t k = 0; k < kLanes; ++k) {                 // join the lanes back into the caller's stream
+    // every exit path: join the lanes back into the caller's stream
+    for (uint32_t k = 0; k < kLanes; ++k)
         if (cudaEventRecord(fence, c->lanes[k]) == cudaSuccess) cudaStreamWaitEvent(st, fence, 0);
-    }
-    for (uint32_t k = 0; k < depth; ++k) cudaEventDestroy(ring[k]);
-    cudaEventDestroy(fence);
     *n_claims = claims;
     if (n_stolen) *n_stolen = stolen_total;
     return result;
+}
+
+int mb_frame_last_stats(double *first_claim_s, double *last_claim_s)
+{
+    if (first_claim_s) *first_claim_s = g_first_claim;
+    if (last_claim_s) *last_claim_s = g_last_claim;
+    return MB_OK;
+}
+
+// ---- band-granular rendering into a shared pinned host frame (8e, end-to-end form) ------------------
+
+int mb_internal_hostframe_region(mb_hostframe *f, void **base, size_t *bytes, int **pinned_flag);   // host_frame.cpp
+
+int mb_hostframe_pin(mb_hostframe *f)
+{
+    void *base = nullptr;
+    size_t bytes = 0;
+    int *pinned = nullptr;
+    if (mb_internal_hostframe_region(f, &base, &bytes, &pinned)) return fail(MB_ERR_INVALID, "NULL frame");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    if (*pinned) return MB_OK;
+    // page-lock this process's mapping of the segment: device->host copies into it are plain DMA
+    MB_CUDA(cudaHostRegister(base, bytes, cudaHostRegisterPortable));
+    *pinned = 1;
+    return MB_OK;
+}
+
+int mb_hostframe_unpin(mb_hostframe *f)
+{
+    void *base = nullptr;
+    size_t bytes = 0;
+    int *pinned = nullptr;
+    if (mb_internal_hostframe_region(f, &base, &bytes, &pinned)) return fail(MB_ERR_INVALID, "NULL frame");
+    if (!*pinned) return MB_OK;
+    MB_CUDA(cudaHostUnregister(base));
+    *pinned = 0;
+    return MB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+constexpr uint32_t kMaxClaim = 64;
+
+// one claim of consecutive band tiles: render into the slot's device staging buffer, then copy
+// every band to its final offset of the host frame (adjacent bands merge into one DMA)
+int claim_to_host(const mb_tile *tiles, uint32_t first, uint32_t got, uint8_t *stage, uint8_t *host, uint64_t host_bytes,
+                  int dtype, cudaStream_t lane)
+{
+    mb_tile tmp[kMaxClaim];
+    size_t off = 0;
+    for (uint32_t k = 0; k < got; ++k) {
+        tmp[k] = tiles[first + k];
+        const size_t sz = (size_t)tmp[k].w * tmp[k].h;
+        if (tmp[k].out_pitch != tmp[k].w) return fail(MB_ERR_INVALID, "tile %u: host-frame bands must be contiguous (out_pitch == w)", first + k);
+        if (tmp[k].out_offset + sz > host_bytes) return fail(MB_ERR_INVALID, "tile %u: band ends beyond the host frame", first + k);
+        tmp[k].out_offset = off;
+        off += sz;
+    }
+    int rc = mb_render_u8(tmp, got, stage, dtype, lane);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < got;) {
+        uint32_t m = k + 1;
+        size_t bytes = (size_t)tmp[k].w * tmp[k].h;
+        while (m < got && tiles[first + m].out_offset == tiles[first + k].out_offset + bytes) { bytes += (size_t)tmp[m].w * tmp[m].h; ++m; }
+        MB_CUDA(cudaMemcpyAsync(host + tiles[first + k].out_offset, stage + tmp[k].out_offset, bytes, cudaMemcpyDeviceToHost, lane));
+        k = m;
+    }
+    return MB_OK;
+}
+
+// shared driver: `next` yields (first, got) claims until it returns 0
+template <typename Next>
+int render_to_host(DeviceCtx *c, const mb_tile *tiles, uint32_t n_tiles, uint32_t bands_per_claim, uint32_t depth,
+                   mb_hostframe *frame, int dtype, uint32_t *claimed, uint32_t max_claims, uint32_t *n_claims,
+                   uint32_t *completed, uint32_t max_completed, uint32_t *n_completed, Next next)
+{
+    constexpr uint32_t kLanes = 4;
+    if (bands_per_claim == 0) bands_per_claim = 1;
+    if (bands_per_claim > kMaxClaim) bands_per_claim = kMaxClaim;
+    if (depth < 2) depth = 2;
+    if (depth > 16) depth = 16;
+    size_t max_band = 0;
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+        const size_t sz = (size_t)tiles[k].w * tiles[k].h;
+        max_band = sz > max_band ? sz : max_band;
+    }
+    const size_t need = max_band * bands_per_claim;
+    for (uint32_t k = 0; k < depth; ++k) {
+        if (c->stage_bytes[k] >= need) continue;
+        if (c->stage[k]) { MB_CUDA(cudaFree(c->stage[k])); c->stage[k] = nullptr; c->stage_bytes[k] = 0; }
+        MB_CUDA(cudaMalloc(&c->stage[k], need));
+        c->stage_bytes[k] = need;
+    }
+    uint8_t *host = mb_hostframe_data(frame);
+    const uint64_t host_bytes = mb_hostframe_bytes(frame);
+    EventSet evs;
+    if (evs.add(depth)) return fail(MB_ERR_CUDA, "cudaEventCreate failed");
+    uint32_t slot_first[16] = {}, slot_got[16] = {};
+    uint32_t claims = 0, retired = 0, done = 0;
+    int result = MB_OK;
+    auto retire = [&](uint32_t k) -> int {               // claim k has landed in host memory: publish it
+        cudaError_t e = cudaEventSynchronize(evs.ev[k % depth]);
+        if (e != cudaSuccess) return fail(MB_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+        return mb_hostframe_mark_done(frame, slot_first[k % depth], slot_got[k % depth], completed, max_completed, &done);
+    };
+    g_first_claim = g_last_claim = now_monotonic();
+    for (;;) {
+        uint32_t first = 0, got = 0;
+        const int pr = next(bands_per_claim, &first, &got);
+        if (pr < 0) { result = pr; break; }
+        if (pr == 0) break;
+        if (claims == 0) g_first_claim = now_monotonic();
+        g_last_claim = now_monotonic();
+        if ((uint64_t)first + got > n_tiles || got > kMaxClaim) { result = fail(MB_ERR_STATE, "bad claim [%u, %u)", first, first + got); break; }
+        if (claimed && claims >= max_claims) { result = fail(MB_ERR_INVALID, "claimed[] too small (%u claims)", max_claims); break; }
+        if (claims >= depth) { if ((result = retire(retired))) break; ++retired; }     // frees this slot's staging buffer
+        cudaStream_t lane = c->lanes[claims % kLanes];
+        if ((result = claim_to_host(tiles, first, got, static_cast<uint8_t *>(c->stage[claims % depth]), host, host_bytes, dtype, lane))) break;
+        cudaError_t e = cudaEventRecord(evs.ev[claims % depth], lane);
+        if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e)); break; }
+        slot_first[claims % depth] = first;
+        slot_got[claims % depth] = got;
+        if (claimed) { claimed[2 * claims] = first; claimed[2 * claims + 1] = got; }
+        ++claims;
+    }
+    for (; retired < claims; ++retired) {                 // drain in submission order, also after an error
+        const int r = retire(retired);
+        if (r && !result) result = r;
+    }
+    if (result) for (uint32_t k = 0; k < kLanes; ++k) cudaStreamSynchronize(c->lanes[k]);
+    if (n_claims) *n_claims = claims;
+    if (n_completed) *n_completed = done;
+    return result;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb_frame_render_u8_host(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_tile *tiles, uint32_t n_tiles,
+                            uint32_t bands_per_claim, uint32_t depth, mb_hostframe *frame, int dtype, uint32_t *claimed,
+                            uint32_t max_claims, uint32_t *n_claims, uint32_t *n_stolen, uint32_t *completed,
+                            uint32_t max_completed, uint32_t *n_completed)
+{
+    if (!q || !tiles || !frame) return fail(MB_ERR_INVALID, "NULL argument");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(MB_ERR_INVALID, "rank %u out of range", rank);
+    if (mb_hostframe_units(frame) != n_tiles) return fail(MB_ERR_INVALID, "the host frame has %u units, the tile list %u", mb_hostframe_units(frame), n_tiles);
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    uint32_t stolen_total = 0;
+    rc = render_to_host(c, tiles, n_tiles, bands_per_claim, depth, frame, dtype, claimed, max_claims, n_claims, completed,
+                        max_completed, n_completed, [&](uint32_t cap, uint32_t *first, uint32_t *got) -> int {
+                            // guided self-scheduling: full claims while plenty is left, single bands at the end
+                            uint32_t want = (uint32_t)(mb_wsq_remaining(q) / ((int64_t)n_ranks * 8));
+                            if (want > cap) want = cap;
+                            if (want == 0) want = 1;
+                            uint32_t stolen = 0;
+                            const int pr = mb_wsq_pop(q, rank, want, first, got, &stolen);
+                            stolen_total += stolen;
+                            return pr;
+                        });
+    if (n_stolen) *n_stolen = stolen_total;
+    return rc;
+}
+
+int mb_frame_render_u8_host_units(const uint32_t *units, uint32_t n_units, const mb_tile *tiles, uint32_t n_tiles,
+                                  uint32_t depth, mb_hostframe *frame, int dtype, uint32_t *completed,
+                                  uint32_t max_completed, uint32_t *n_completed)
+{
+    if (!tiles || !frame || (!units && n_units)) return fail(MB_ERR_INVALID, "NULL argument");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    uint32_t pos = 0;
+    return render_to_host(c, tiles, n_tiles, 1, depth, frame, dtype, nullptr, 0, nullptr, completed, max_completed, n_completed,
+                          [&](uint32_t, uint32_t *first, uint32_t *got) -> int {
+                              if (pos >= n_units) return 0;
+                              *first = units[pos++];
+                              *got = 1;
+                              return 1;
+                          });
 }
 
 // ---- serialisation (f2) --------------------------------------------------------------------
@@ -678,6 +922,7 @@ int mb_process_workload_serialized(uint32_t level, uint32_t mrd, uint32_t index_
     mb_tile t;
     int rc = mb_chunk_geometry(level, index_real, index_imag, definition, mrd, &t);
     if (rc) return rc;
+    t.flags = g_tile_flags;
     const size_t n = (size_t)definition * definition;
     if (out_capacity < n + 1) return fail(MB_ERR_INVALID, "out_capacity must be >= definition^2 + 1");
     DeviceCtx *c = nullptr;

@@ -35,6 +35,7 @@ class FrameSpec:
     mrd: int
     dtype: str = "f64"
     band_rows: int = 256          # rows per dispatch unit (a band is contiguous in the chunk layout)
+    shortcut: bool = False        # MB_TILE_PERIOD_SHORTCUT on every band (bit-identical counts, fewer executed updates)
 
     @property
     def n_chunks(self) -> int:
@@ -74,7 +75,7 @@ def frame_bands(spec: FrameSpec):
     d = spec.definition
     tiles, extents = [], []
     for c, (ir, ii) in enumerate(spec.chunk_indices()):
-        chunk = nat.chunk_geometry(spec.level, ir, ii, d, spec.mrd)
+        chunk = nat.chunk_geometry(spec.level, ir, ii, d, spec.mrd, shortcut=spec.shortcut)
         for y0 in range(0, d, spec.band_rows):
             h = min(spec.band_rows, d - y0)
             off = c * d * d + y0 * d
@@ -261,3 +262,146 @@ def shared_frame_buffer(spec: FrameSpec, rank: int, device: int, group=None):
 
 def queue_name() -> str:
     return f"/mbq_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+
+
+# ---- end-to-end in-box path: band-granular dispatch into ONE shared pinned host frame ----------------
+
+def workload_bands(workloads, definition: int, band_rows: int, shortcut: bool = False):
+    """Row-band tiles for a list of (level, mrd, index_real, index_imag) workloads.  Band k of chunk c
+    is unit c * bands_per_chunk + k of the host frame; out_offset is its BYTE offset in the frame of
+    uint8 payloads (chunk c's payload = bytes [c*d*d, (c+1)*d*d), exactly process_workload's output)."""
+    d = int(definition)
+    tiles = []
+    for c, (level, mrd, ir, ii) in enumerate(workloads):
+        chunk = nat.chunk_geometry(level, ir, ii, d, mrd, shortcut=shortcut)
+        for y0 in range(0, d, band_rows):
+            h = min(band_rows, d - y0)
+            tiles.append(chunk.sub(0, y0, d, h, c * d * d + y0 * d, d))
+    return nat.tile_array(tiles), (d + band_rows - 1) // band_rows
+
+
+class InboxWorker:
+    """process_workloads for ALL GPUs of one box (SURVEY.md 8e + f4): the same uint8 payloads, one
+    per (level, mrd, index_real, index_imag), but a chunk is no longer the unit of work.
+
+    Behind the reference's worker API a DataChunk cannot be split, so one 50 000-iteration chunk
+    (0.3 s) bounds an 8-GPU frame.  Here every chunk is cut into row bands, the bands of all chunks go
+    through the shared work-stealing queue (csrc/tile_wsq.cpp), and every rank copies its bands
+    device->host straight to their final offsets of ONE page-locked shm frame
+    (csrc/host_frame.cpp): no gather, no second copy; a payload is complete when its band counter
+    hits zero, and `consume(workload, payload)` is called for it while other chunks still render.
+    Bands claimed by a rank that died are found by `missing()` and rendered again by `repair()`.
+
+    One instance per process; rank 0 creates the segments, `barrier` (e.g. torch.distributed.barrier)
+    separates create from open.  `launch(first, count, frame_array)` is a CPU test hook that replaces
+    the CUDA dispatch loop."""
+
+    def __init__(self, workloads, definition: int = nat.CHUNK_DEFINITION, band_rows: int = 256, rank: int = 0,
+                 world: int = 1, device: Optional[int] = None, name: Optional[str] = None, barrier: Optional[Callable] = None,
+                 shortcut: bool = False, dtype: str = "f64", bands_per_claim: int = 4, depth: int = 6,
+                 launch: Optional[Callable] = None):
+        self.workloads = [tuple(int(v) for v in w) for w in workloads]
+        self.definition, self.band_rows = int(definition), int(band_rows)
+        self.rank, self.world, self.dtype = rank, world, dtype
+        self.bands_per_claim, self.depth = bands_per_claim, depth
+        self._barrier = barrier if barrier is not None else (lambda: None)
+        self._launch = launch
+        if launch is None:
+            nat.ensure_init(device)
+        self.tiles, self.bands_per_chunk = workload_bands(self.workloads, self.definition, self.band_rows, shortcut)
+        self.n_bands = len(self.tiles)
+        self.chunk_bytes = self.definition * self.definition
+        name = name or queue_name()
+        qn, fn = name + "_bq", name + "_hf"
+        if rank == 0:
+            self.queue = nat.TileQueue(qn, world, self.n_bands, create=True)
+            self.frame = nat.HostFrame(fn, len(self.workloads) * self.chunk_bytes, self.n_bands, self.bands_per_chunk, create=True)
+        self._barrier()
+        if rank != 0:
+            self.queue = nat.TileQueue(qn)
+            self.frame = nat.HostFrame(fn)
+        if launch is None:
+            self.frame.pin()                 # cudaHostRegister on this rank's mapping: D2H at PCIe speed
+        self.steals = self.claims = 0
+        self.completed: List[int] = []
+
+    def rearm(self) -> None:
+        """Prepare another pass over the same workloads (collective: every rank calls it)."""
+        self._barrier()
+        if self.rank == 0:
+            self.queue.reset(self.n_bands)
+            self.frame.reset()
+        self._barrier()
+
+    def payload(self, k: int):
+        """uint8[definition^2] view of workload k's payload in the shared frame."""
+        return self.frame.array[k * self.chunk_bytes:(k + 1) * self.chunk_bytes]
+
+    def render(self, consume: Optional[Callable] = None) -> List[int]:
+        """Claim bands until the queue is drained; returns when every band THIS rank claimed has landed
+        in host memory.  -> indices of the workloads whose last band this rank delivered; `consume` is
+        called for each of them (the frame is complete on all ranks only after the next barrier)."""
+        if self._launch is not None:
+            done = self._render_hook()
+        else:
+            cap = self.n_bands
+            claimed = (C.c_uint32 * (2 * cap))()
+            comp = (C.c_uint32 * len(self.workloads))()
+            n_claims, n_stolen, n_comp = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            nat.check(nat.lib().mb_frame_render_u8_host(
+                self.queue._h, self.rank, self.world, self.tiles, self.n_bands, self.bands_per_claim, self.depth,
+                self.frame._h, nat.DTYPES[self.dtype], claimed, cap, C.byref(n_claims), C.byref(n_stolen),
+                comp, len(self.workloads), C.byref(n_comp)))
+            self.claims += n_claims.value
+            self.steals += n_stolen.value
+            done = [comp[k] for k in range(n_comp.value)]
+        self.completed = done
+        if consume is not None:
+            for g in done:
+                consume(self.workloads[g], self.payload(g))
+        return done
+
+    def _render_hook(self) -> List[int]:
+        done: List[int] = []
+        while True:
+            want = max(1, min(self.bands_per_claim, self.queue.remaining() // (self.world * 8)))
+            got = self.queue.pop(self.rank, want)
+            if got is None:
+                return done
+            first, cnt, stolen = got
+            self.steals += int(stolen)
+            self.claims += 1
+            if self._launch(first, cnt, self.frame.array) is False:
+                continue                     # test hook: a rank that "died" after claiming
+            done += self.frame.mark_done(first, cnt)
+
+    def missing(self) -> List[int]:
+        """Bands no rank delivered (call after the barrier that follows render())."""
+        return self.frame.missing()
+
+    def repair(self, consume: Optional[Callable] = None) -> List[int]:
+        """Render the bands `missing()` reports on this rank; -> workloads completed by it."""
+        units = self.missing()
+        if not units:
+            return []
+        if self._launch is not None:
+            done: List[int] = []
+            for u in units:
+                self._launch(u, 1, self.frame.array)
+                done += self.frame.mark_done(u, 1)
+        else:
+            arr = (C.c_uint32 * len(units))(*units)
+            comp = (C.c_uint32 * len(self.workloads))()
+            n_comp = C.c_uint32()
+            nat.check(nat.lib().mb_frame_render_u8_host_units(arr, len(units), self.tiles, self.n_bands, self.depth, self.frame._h,
+                                                              nat.DTYPES[self.dtype], comp, len(self.workloads), C.byref(n_comp)))
+            done = [comp[k] for k in range(n_comp.value)]
+        if consume is not None:
+            for g in done:
+                consume(self.workloads[g], self.payload(g))
+        return done
+
+    def close(self) -> None:
+        self._barrier()
+        self.frame.close()
+        self.queue.close()

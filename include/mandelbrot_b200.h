@@ -69,8 +69,19 @@ typedef struct mb_tile {
     uint32_t x0, y0, w, h;
     uint64_t out_offset;   /* in elements */
     uint32_t out_pitch;    /* elements between successive tile rows in out */
-    uint32_t flags;        /* reserved, must be 0 */
+    uint32_t flags;        /* 0, or MB_TILE_PERIOD_SHORTCUT; the same for every tile of one launch */
 } mb_tile;                 /* 88 bytes */
+
+/*
+ * mb_tile.flags bit 0 -- exact orbit-periodicity shortcut (opt-in, off by default).  A lane whose
+ * (x, y) state at a block end is BIT-EQUAL to an earlier block-end state is on an exact cycle of
+ * the floating-point map; it can never escape, so the reference loop (.py:47-68) would run to
+ * mrd-1 and return 0 -- the lane reports 0 at once.  Counts are bit-identical with the flag on
+ * or off; only the number of EXECUTED updates drops (pixels inside the set dominate the deep
+ * zooms).  Throughput measured with the flag is reported separately from the FP64-pipe roofline
+ * numbers, which always count executed work.
+ */
+#define MB_TILE_PERIOD_SHORTCUT 1u
 
 /* ---- lifecycle ----------------------------------------------------------------------- */
 
@@ -83,6 +94,18 @@ int mb_abi_version(void);
 int mb_device_count(void);
 /* SM count of the bound device (148 on B200) */
 int mb_sm_count(void);
+/*
+ * Per-thread switch for the one-call entry points below (mb_process_workload_*): render their
+ * chunk with MB_TILE_PERIOD_SHORTCUT (see mb_tile.flags; results are bit-identical either way).
+ * Off by default.  Returns the previous setting.  Tile-array entry points take the flag per tile.
+ */
+int mb_set_period_shortcut(int enabled);
+/*
+ * Diagnostic for shortcut launches of THIS thread: counter_dev (device uint64, caller-zeroed, NULL
+ * to disable) accumulates the updates the kernel actually executed, to be set against
+ * mb_useful_iterations (the updates the reference semantics require).
+ */
+int mb_set_executed_counter(uint64_t *counter_dev);
 
 /* ---- geometry (host only, no GPU needed) --------------------------------------------- */
 
@@ -256,6 +279,66 @@ int mb_frame_render_stolen(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_
                            uint32_t n_tiles, uint32_t bands_per_claim, uint32_t depth,
                            int32_t *out_dev, int dtype, void *stream, uint32_t *claimed,
                            uint32_t max_claims, uint32_t *n_claims, uint32_t *n_stolen);
+
+/* wall-clock (CLOCK_MONOTONIC, seconds) of the calling thread's last dispatch loop: when its first and
+ * its last claim were taken -- with the caller's own end-of-step time this gives the queue-drain
+ * tail (last claim -> last kernel end) that names the scaling limiter (bench.py) */
+int mb_frame_last_stats(double *first_claim_s, double *last_claim_s);
+
+/* ---- one frame of DataChunk payloads in shared, page-locked host memory ----------------------- */
+/*
+ * End-to-end form of the in-box path: the uint8 payloads of a frame (what process_workload
+ * returns per chunk, .py:70-100; DataChunk.cs:20,27) live ONCE in a POSIX shm segment that every
+ * GPU process of the box maps and page-locks.  The unit of dispatch is a row band ("unit"), so one
+ * expensive chunk is rendered by several GPUs; every band is copied device->host straight to its
+ * final offset of its chunk ("group" = `units_per_group` consecutive units) -- no gather, no
+ * second copy.  Replaces the per-chunk TCP return of Distributer.cs:400-458 inside one box.
+ * unit_done / group_left counters in the segment tell which payloads are complete and which
+ * bands a dead rank left behind (mb_hostframe_missing; the reference's answer is its lease
+ * timeout, Distributer.cs:22,317-330).  Host-only except mb_hostframe_pin/unpin.
+ */
+typedef struct mb_hostframe mb_hostframe;
+int mb_hostframe_create(const char *name, uint64_t payload_bytes, uint32_t n_units,
+                        uint32_t units_per_group, mb_hostframe **out);   /* one rank; name like "/mbf_1" */
+int mb_hostframe_open(const char *name, mb_hostframe **out);              /* the others, after a barrier */
+uint8_t *mb_hostframe_data(mb_hostframe *f);                              /* payload area of this mapping */
+uint64_t mb_hostframe_bytes(mb_hostframe *f);
+uint32_t mb_hostframe_units(mb_hostframe *f);
+uint32_t mb_hostframe_groups(mb_hostframe *f);
+int mb_hostframe_reset(mb_hostframe *f);                                  /* re-arm for another pass (one rank, between barriers) */
+/* page-lock / unlock THIS process's mapping on the bound device (cudaHostRegister) */
+int mb_hostframe_pin(mb_hostframe *f);
+int mb_hostframe_unpin(mb_hostframe *f);
+/*
+ * Publish units [first_unit, first_unit + count) as landed.  Groups whose last unit this was are
+ * appended to completed[] (capacity max_completed); *n_completed is incremented per such group
+ * (it is NOT reset: pass a zeroed counter).  Idempotent per unit.
+ */
+int mb_hostframe_mark_done(mb_hostframe *f, uint32_t first_unit, uint32_t count, uint32_t *completed,
+                           uint32_t max_completed, uint32_t *n_completed);
+int64_t mb_hostframe_group_left(mb_hostframe *f, uint32_t group);         /* units still missing */
+/* units not (yet) landed: after the queue is drained and every live rank has returned, these were
+ * claimed by a rank that died; units[] may be NULL to only count */
+int mb_hostframe_missing(mb_hostframe *f, uint32_t *units, uint32_t max_units, uint32_t *n_missing);
+int mb_hostframe_close(mb_hostframe *f);
+int mb_hostframe_unlink(const char *name);
+
+/*
+ * Per-GPU dispatch loop of the end-to-end in-box path: like mb_frame_render_stolen, but every
+ * claim is rendered with the fused uint8 epilogue (.py:96-98) into a device staging ring and copied
+ * to tiles[k].out_offset (BYTES) of the host frame; tile k is unit k, its rows must be contiguous
+ * (out_pitch == w).  Returns when every band this rank claimed has LANDED in host memory and is
+ * published (mb_hostframe_mark_done); completed[] receives the chunks this rank completed.
+ */
+int mb_frame_render_u8_host(mb_wsq *q, uint32_t rank, uint32_t n_ranks, const mb_tile *tiles,
+                            uint32_t n_tiles, uint32_t bands_per_claim, uint32_t depth,
+                            mb_hostframe *frame, int dtype, uint32_t *claimed, uint32_t max_claims,
+                            uint32_t *n_claims, uint32_t *n_stolen, uint32_t *completed,
+                            uint32_t max_completed, uint32_t *n_completed);
+/* same for an explicit list of units (repairing what mb_hostframe_missing reported) */
+int mb_frame_render_u8_host_units(const uint32_t *units, uint32_t n_units, const mb_tile *tiles,
+                                  uint32_t n_tiles, uint32_t depth, mb_hostframe *frame, int dtype,
+                                  uint32_t *completed, uint32_t max_completed, uint32_t *n_completed);
 
 /* ---- frame buffer shared between the GPU processes of one box (peer memory over NVLink) ------- */
 /*

@@ -85,6 +85,20 @@ uint64_t mbo_fnv1a_words(const int32_t *counts, size_t n);
 
 int mbo_max_threads(void);
 
+/*
+ * Data-parallel build of the same restatement (mandel_oracle_simd.c): 8 / 16 pixels of a row per
+ * vector, lane-wise IEEE operations, no contraction -- bit-identical to mbo_render_rect /
+ * mbo_render_frame by construction and by test (tests/test_oracle_golden.py).  Fast enough to
+ * render whole native chunks of the BASELINE frames (oracle/gen_fullsize_golden.py).
+ */
+int mbo_simd_render_rect(double start_r, double start_i, double range, uint32_t d, int32_t mrd,
+                         uint32_t x0, uint32_t y0, uint32_t w, uint32_t h,
+                         int32_t *out, size_t pitch, int dtype, int threads);
+int mbo_simd_render_frame(uint32_t level, uint32_t ir0, uint32_t ii0, uint32_t blocks, uint32_t d,
+                          int32_t mrd, int dtype, int threads, int32_t *out, uint64_t *useful);
+/* vector width (bits) of the body the loader selected for this CPU: 512, 256 or 128 */
+int mbo_simd_width(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,9 +22,8 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc -O2 -ffp-contract=off)."""
-    src = os.path.join(_HERE, "mandel_oracle.c")
-    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "mandel_oracle.h")))
+    srcs = [os.path.join(_HERE, f) for f in ("mandel_oracle.c", "mandel_oracle_simd.c", "mandel_oracle.h", "Makefile")]
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libmandel_oracle.so"])
     return _SO
@@ -66,6 +65,12 @@ def lib() -> C.CDLL:
         L.mbo_fnv1a_words.restype = u64
         L.mbo_max_threads.argtypes = []
         L.mbo_max_threads.restype = C.c_int
+        L.mbo_simd_render_rect.argtypes = L.mbo_render_rect.argtypes
+        L.mbo_simd_render_rect.restype = C.c_int
+        L.mbo_simd_render_frame.argtypes = L.mbo_render_frame.argtypes
+        L.mbo_simd_render_frame.restype = C.c_int
+        L.mbo_simd_width.argtypes = []
+        L.mbo_simd_width.restype = C.c_int
         _lib = L
     return _lib
 
@@ -91,22 +96,28 @@ def escape_f64(r: float, i: float, mrd: int) -> int:
     return int(lib().mbo_escape_f64(r, i, mrd))
 
 
-def render_rect(start_r, start_i, rng, d, mrd, x0=0, y0=0, w=None, h=None, dtype="f64", threads=0) -> np.ndarray:
-    """int32 counts [h, w] for the sub-rectangle of the chunk-level linspace grid."""
+def render_rect(start_r, start_i, rng, d, mrd, x0=0, y0=0, w=None, h=None, dtype="f64", threads=0,
+                simd=False) -> np.ndarray:
+    """int32 counts [h, w] for the sub-rectangle of the chunk-level linspace grid.
+    simd=True: the data-parallel build of the same loop (mandel_oracle_simd.c), bit-identical."""
     w = d - x0 if w is None else w
     h = d - y0 if h is None else h
     out = np.empty((h, w), dtype=np.int32)
-    rc = lib().mbo_render_rect(start_r, start_i, rng, d, mrd, x0, y0, w, h, _p(out, C.c_int32), w,
-                               {"f64": 0, "f32": 1}[dtype], threads)
+    fn = lib().mbo_simd_render_rect if simd else lib().mbo_render_rect
+    rc = fn(start_r, start_i, rng, d, mrd, x0, y0, w, h, _p(out, C.c_int32), w, {"f64": 0, "f32": 1}[dtype], threads)
     if rc != 0:
         raise ValueError(f"mbo_render_rect failed rc={rc}")
     return out
 
 
 def render_chunk_counts(level, mrd, index_real, index_imag, d=4096, dtype="f64", threads=0,
-                        x0=0, y0=0, w=None, h=None) -> np.ndarray:
+                        x0=0, y0=0, w=None, h=None, simd=False) -> np.ndarray:
     rng, sr, si = chunk_geometry(level, index_real, index_imag)
-    return render_rect(sr, si, rng, d, mrd, x0, y0, w, h, dtype, threads)
+    return render_rect(sr, si, rng, d, mrd, x0, y0, w, h, dtype, threads, simd)
+
+
+def simd_width() -> int:
+    return int(lib().mbo_simd_width())
 
 
 def process_workload(level, mrd, index_real, index_imag, d=4096, threads=0, want_counts=False):
@@ -120,11 +131,11 @@ def process_workload(level, mrd, index_real, index_imag, d=4096, threads=0, want
     return (out, counts) if want_counts else out
 
 
-def render_frame(level, ir0, ii0, blocks, d, mrd, dtype="f64", threads=0, want_counts=True):
+def render_frame(level, ir0, ii0, blocks, d, mrd, dtype="f64", threads=0, want_counts=True, simd=False):
     """Whole frame on all cores -> (counts[blocks*blocks, d, d] or None, useful pixel-iterations)."""
     out = np.empty((blocks * blocks, d, d), dtype=np.int32) if want_counts else None
     useful = C.c_uint64()
-    rc = lib().mbo_render_frame(level, ir0, ii0, blocks, d, mrd, {"f64": 0, "f32": 1}[dtype], threads,
+    rc = (lib().mbo_simd_render_frame if simd else lib().mbo_render_frame)(level, ir0, ii0, blocks, d, mrd, {"f64": 0, "f32": 1}[dtype], threads,
                                 _p(out, C.c_int32) if want_counts else None, C.byref(useful))
     if rc != 0:
         raise ValueError(f"mbo_render_frame failed rc={rc}")

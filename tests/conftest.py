@@ -53,3 +53,18 @@ def gpu(native):
         pytest.skip("no CUDA device on this box")
     native.init(0)
     return native
+
+
+def load_fullsize(name: str):
+    """tests/golden/fullsize_<name>.json: per-chunk digests of a BASELINE frame at its full size,
+    produced by the CPU oracle alone (oracle/gen_fullsize_golden.py)."""
+    path = os.path.join(GOLDEN, f"fullsize_{name}.json")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    with open(path) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def fullsize():
+    return load_fullsize

@@ -158,3 +158,78 @@ def test_escaped_stays_escaped_property(oracle):
     rad2 = 4.0 + rng.choice([-1, 1], n) * 2.0 ** rng.uniform(-9, -3, n)
     rad = np.sqrt(rad2)
     assert oracle.sticky_violations_f32(rad * np.cos(th), rad * np.sin(th), 300, extra=15, band=2.0 ** -9) == 0
+
+
+# ---- the data-parallel build of the oracle and the full-size digests it produced ---------------
+
+def test_simd_oracle_equals_scalar_oracle(oracle):
+    """mandel_oracle_simd.c (8/16 pixels per vector, lane-wise IEEE ops) is bit-identical to the
+    scalar restatement: ragged widths (padding path), every mrd around small values, both dtypes,
+    boundary tiles of all BASELINE windows, sub-rectangles, and one thread vs many."""
+    cases = [(1, 0, 0, 131, 300, "f64"), (2, 1, 0, 97, 1000, "f64"), (10, 3, 5, 200, 1024, "f64"), (16, 4, 8, 64, 1024, "f64"),
+             (800, 250, 420, 100, 10000, "f64"), (4000000, 1256355, 2131824, 48, 50000, "f64"), (5, 4, 4, 101, 200, "f64"),
+             (4, 1, 1, 150, 4096, "f32"), (4, 2, 1, 77, 700, "f32"), (1, 0, 0, 129, 333, "f32"), (7, 6, 0, 2, 5, "f64"),
+             (5, 2, 2, 1, 100, "f64"), (3, 0, 2, 17, 1, "f32"), (3, 0, 2, 33, 2, "f64")]
+    for (level, ir, ii, d, mrd, dt) in cases:
+        a = oracle.render_chunk_counts(level, mrd, ir, ii, d, dtype=dt)
+        b = oracle.render_chunk_counts(level, mrd, ir, ii, d, dtype=dt, simd=True)
+        assert np.array_equal(a, b), (level, ir, ii, d, mrd, dt)
+        c = oracle.render_chunk_counts(level, mrd, ir, ii, d, dtype=dt, simd=True, threads=1)
+        assert np.array_equal(a, c)
+    for mrd in range(0, 40):
+        for dt in ("f64", "f32"):
+            assert np.array_equal(oracle.render_chunk_counts(10, mrd, 3, 5, 37, dtype=dt),
+                                  oracle.render_chunk_counts(10, mrd, 3, 5, 37, dtype=dt, simd=True)), (mrd, dt)
+    a = oracle.render_chunk_counts(10, 500, 3, 5, 300, x0=13, y0=250, w=55, h=9)
+    assert np.array_equal(a, oracle.render_chunk_counts(10, 500, 3, 5, 300, x0=13, y0=250, w=55, h=9, simd=True))
+    assert oracle.simd_width() in (128, 256, 512)
+    _, u0 = oracle.render_frame(16, 0, 0, 4, 32, 200, want_counts=False)
+    f1, u1 = oracle.render_frame(16, 0, 0, 4, 32, 200, simd=True)
+    assert u0 == u1 == sum(oracle.useful_iterations(f1[c], 200) for c in range(16))
+
+
+def test_simd_oracle_reproduces_the_reference_text_goldens(oracle, golden_meta, golden_arrays):
+    """... and therefore the fixtures generated by executing the reference's own function text."""
+    for rec in golden_meta["small"]:
+        got = oracle.render_chunk_counts(rec["level"], rec["mrd"], rec["ir"], rec["ii"], rec["d"], simd=True)
+        assert np.array_equal(got, golden_arrays[rec["key"] + "_counts"]), rec
+    for rec in golden_meta["medium"]:
+        if rec["d"] > 1024:
+            continue
+        got = oracle.render_chunk_counts(rec["level"], rec["mrd"], rec["ir"], rec["ii"], rec["d"], simd=True)
+        assert oracle.useful_iterations(got, rec["mrd"]) == rec["useful"] and f"{oracle.fnv1a_words(got):016x}" == rec["fnv"], rec
+
+
+def test_fullsize_fixture_matches_the_frame_table(oracle):
+    """tests/golden/fullsize_*.json: the generator's frame parameters are the product's CONFIGS, the
+    chunk order is the product's, and the cheap chunks re-digest to the stored values right here."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from distributedmandelbrot_b200.frame import CONFIGS
+    seen = 0
+    for name in ("cfg2", "cfg3", "cfg4", "cfg5"):
+        path = os.path.join(GOLDEN, f"fullsize_{name}.json")
+        if not os.path.exists(path):
+            continue
+        doc = json.load(open(path))
+        spec, fr = CONFIGS[name], doc["frame"]
+        assert (spec.level, spec.blocks, spec.definition, spec.ir0, spec.ii0, spec.mrd, spec.dtype) == \
+            (fr["level"], fr["blocks"], fr["definition"], fr["ir0"], fr["ii0"], fr["mrd"], fr["dtype"])
+        idx = spec.chunk_indices()
+        for c, rec in doc["chunks"].items():
+            assert (rec["ir"], rec["ii"]) == idx[int(c)]
+        if doc.get("complete"):
+            assert len(doc["chunks"]) == spec.n_chunks
+            assert doc["useful_total"] == sum(r["useful"] for r in doc["chunks"].values())
+        # re-digest the two cheapest chunks (a few 1e7..1e9 pixel-iterations) with the SCALAR oracle
+        cheap = sorted(doc["chunks"].values(), key=lambda r: r["useful"])[:2]
+        for rec in cheap:
+            if rec["useful"] > 4e9:
+                continue
+            got = oracle.render_chunk_counts(spec.level, spec.mrd, rec["ir"], rec["ii"], spec.definition, dtype=spec.dtype)
+            assert oracle.useful_iterations(got, spec.mrd) == rec["useful"]
+            assert f"{oracle.fnv1a_words(got):016x}" == rec["fnv"]
+            assert int((got == 0).sum()) == rec["zeros"] and int(got.max()) == rec["max"]
+            seen += 1
+    assert seen > 0
