@@ -210,8 +210,13 @@ def main() -> None:
                          "into rank 0's frame buffer over NVLink peer memory (no gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shortcut", action="store_true", help="skip the separately reported periodicity-shortcut legs")
+    ap.add_argument("--refill", type=int, default=None, choices=[0, 1],
+                    help="1 = persistent-warp kernel with lane refill (MB_TILE_LANE_REFILL), 0 = one warp per 8x4 patch; "
+                         "default: the workload's own setting (frame.CONFIGS)")
     args = ap.parse_args()
     spec = get_spec(args.workload)
+    if args.refill is not None:
+        spec = spec.scaled(refill=bool(args.refill))
     if args.impl == "reference":
         run_reference(args, spec)
         return
@@ -390,17 +395,17 @@ def main() -> None:
         def run_e2e(use_shortcut: bool):
             secs = []
             if world == 1:
-                worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None, shortcut=use_shortcut)   # warm the pinned ring
+                worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None, shortcut=use_shortcut, refill=spec.refill)   # warm the pinned ring
                 for _ in range(args.e2e_steps):
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    worker.process_workloads(wl_all, definition=spec.definition, consume=consume, shortcut=use_shortcut)
+                    worker.process_workloads(wl_all, definition=spec.definition, consume=consume, shortcut=use_shortcut, refill=spec.refill)
                     torch.cuda.synchronize()
                     secs.append(time.perf_counter() - t0)
                 return secs, "worker.process_workloads (uint8 DataChunk payloads in pinned host memory, one per (level, mrd, ir, ii))"
             iw = InboxWorker(wl_all, definition=spec.definition, band_rows=spec.band_rows, rank=rank, world=world, device=local,
                              name=queue_name() + ("_s" if use_shortcut else "_e"), barrier=dist.barrier, shortcut=use_shortcut,
-                             bands_per_claim=4, depth=6)
+                             bands_per_claim=4, depth=6, refill=spec.refill)
             iw.rearm()
             iw.render()                                        # warm-up pass (staging buffers, page-locked mapping)
             for _ in range(args.e2e_steps):
@@ -451,6 +456,7 @@ def main() -> None:
                        "definition": spec.definition, "ir0": spec.ir0, "ii0": spec.ii0, "mrd": spec.mrd,
                        "pixels": spec.pixels, "useful_pixel_iterations": useful,
                        "mean_iterations_per_pixel": useful / spec.pixels, "band_rows": spec.band_rows,
+                       "kernel": "escape_refill_kernel (persistent warps, lane refill)" if spec.refill else "escape_tiles_kernel (one warp per 8x4 patch)",
                        "parallelism": "1 GPU, one launch over all bands" if world == 1 else
                                       f"{world} GPUs, shm work-stealing bands + " + ("one batched NCCL send/recv gather to rank 0" if shared_out is None
                                                                                       else "kernel stores directly into rank 0's buffer over NVLink peer memory"),

@@ -19,6 +19,7 @@ DTYPE_F64, DTYPE_F32 = 0, 1
 DTYPES = {"f64": DTYPE_F64, "f32": DTYPE_F32, DTYPE_F64: DTYPE_F64, DTYPE_F32: DTYPE_F32}
 CHUNK_DEFINITION = 4096   # DataChunk.dataChunkRange (DataChunk.cs:20) ; .py:80
 TILE_PERIOD_SHORTCUT = 1  # mb_tile.flags bit 0: exact orbit-periodicity shortcut (bit-identical counts)
+TILE_LANE_REFILL = 2      # mb_tile.flags bit 1: persistent warps with lane refill (bit-identical counts; for deep zooms)
 
 
 class NativeError(RuntimeError):
@@ -82,6 +83,7 @@ SIGNATURES = {
     "mb_device_count": (_int, []),
     "mb_sm_count": (_int, []),
     "mb_set_period_shortcut": (_int, [_int]),
+    "mb_set_tile_flags": (_int, [_u32]),
     "mb_set_executed_counter": (_int, [_vp]),
     "mb_frame_last_stats": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mb_hostframe_create": (_int, [C.c_char_p, _u64, _u32, _u32, C.POINTER(_vp)]),
@@ -193,8 +195,13 @@ def set_period_shortcut(enabled: bool) -> bool:
     return bool(lib().mb_set_period_shortcut(1 if enabled else 0))
 
 
+def set_tile_flags(flags: int) -> int:
+    """Flag word (TILE_PERIOD_SHORTCUT | TILE_LANE_REFILL) of this thread's one-call entry points; -> previous."""
+    return check(lib().mb_set_tile_flags(int(flags)))
+
+
 def chunk_geometry(level: int, index_real: int, index_imag: int, definition: int = CHUNK_DEFINITION,
-                   mrd: int = 0, shortcut: bool = False) -> Tile:
+                   mrd: int = 0, shortcut: bool = False, refill: bool = False) -> Tile:
     """Whole-chunk tile descriptor (.py:75-78 + linspace parameters of .py:24-32).  Host only.
     shortcut=True sets MB_TILE_PERIOD_SHORTCUT on the tile (and on every sub-tile cut from it)."""
     for name, v in (("level", level), ("index_real", index_real), ("index_imag", index_imag),
@@ -203,8 +210,7 @@ def chunk_geometry(level: int, index_real: int, index_imag: int, definition: int
             raise InvalidArgument(MB_ERR_INVALID, f"{name}={v} is not a uint32")
     t = Tile()
     check(lib().mb_chunk_geometry(int(level), int(index_real), int(index_imag), int(definition), int(mrd), C.byref(t)))
-    if shortcut:
-        t.flags = TILE_PERIOD_SHORTCUT
+    t.flags = (TILE_PERIOD_SHORTCUT if shortcut else 0) | (TILE_LANE_REFILL if refill else 0)
     return t
 
 

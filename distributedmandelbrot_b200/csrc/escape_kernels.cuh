@@ -45,7 +45,14 @@ template <> struct Ops<double> {
     // m >= 4.0 for finite m >= 0  <=>  hi32(m) >= hi32(4.0)
     static __device__ __forceinline__ bool escaped(double m) { return __double2hiint(m) >= 0x40100000; }
     static __device__ __forceinline__ double coord(double v) { return v; }
-    static __device__ __forceinline__ bool ordinary(double cr, double ci) { return fabs(cr) <= 4.0 && fabs(ci) <= 4.0; }
+    // Coordinates for which fma(fl(x*y), 2, ci) == fl(fl((2x)*y) + ci) is guaranteed: no overflow of 2x
+    // (|c| <= 4, see Appendix A) and no visible underflow of x*y: when x*y is subnormal, fl(xy)*2 and
+    // fl(2xy) may differ by 2^-1074, which a non-zero ci >= 2^-500 absorbs (the difference is > 500
+    // binary orders below half an ulp of the sum and cannot reach a rounding tie), and ci == 0 keeps
+    // y == 0 for good.  A non-zero |ci| < 2^-500 (reachable only through calc_mb_value) takes the
+    // literal (2x)*y path instead; cr is held to the same rule for symmetry.
+    static __device__ __forceinline__ bool tiny(double v) { return v != 0.0 && fabs(v) < 3.0549363634996047e-151; }   // 2^-500
+    static __device__ __forceinline__ bool ordinary(double cr, double ci) { return fabs(cr) <= 4.0 && fabs(ci) <= 4.0 && !tiny(cr) && !tiny(ci); }
     static __device__ __forceinline__ bool ge4(double m) { return m >= 4.0; }     // IEEE compare: false for NaN
     // bit equality on the ALU pipe (integer compares; an FP compare would cost an FP64-pipe slot)
     static __device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
@@ -59,7 +66,8 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ bool escaped(float m) { return __float_as_int(m) >= 0x40800000; }
     // Appendix A.5: the binary64 linspace value rounded once to binary32
     static __device__ __forceinline__ float coord(double v) { return __double2float_rn(v); }
-    static __device__ __forceinline__ bool ordinary(float cr, float ci) { return fabsf(cr) <= 4.0f && fabsf(ci) <= 4.0f; }
+    static __device__ __forceinline__ bool tiny(float v) { return v != 0.0f && fabsf(v) < 8.673617379884035e-19f; }        // 2^-60
+    static __device__ __forceinline__ bool ordinary(float cr, float ci) { return fabsf(cr) <= 4.0f && fabsf(ci) <= 4.0f && !tiny(cr) && !tiny(ci); }
     static __device__ __forceinline__ bool ge4(float m) { return m >= 4.0f; }
     static __device__ __forceinline__ bool same_bits(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
 };
@@ -264,6 +272,10 @@ struct TileArgs {
     uint32_t n_inline;
     uint32_t pad;
     unsigned long long *executed;       // PERIOD only, may be NULL: += updates actually executed
+    unsigned long long *counter;        // escape_refill_kernel: the launch's patch counter (zeroed before the launch)
+    uint32_t n_tiles;                   // escape_refill_kernel: tiles in this launch ...
+    uint32_t pcols, prows;              // ... and patch slots per tile (max over the launch's tiles)
+    uint32_t pad2;
     mb_tile inl[kInlineTiles];
 };
 

@@ -18,6 +18,7 @@
 
 #include "chunk_codec.cuh"
 #include "escape_kernels.cuh"
+#include "escape_refill.cuh"
 
 namespace {
 
@@ -64,6 +65,8 @@ struct DeviceCtx {
     cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};   // concurrent launch lanes of the dispatch loop
     void *scratch = nullptr;            // device output buffer of the host-buffer entry points
     size_t scratch_bytes = 0;
+    unsigned long long *counters = nullptr;   // patch counters of the lane-refill kernel, one per launch in flight
+    uint32_t next_counter = 0;
     void *stage[16] = {};               // per-slot device staging of mb_frame_render_u8_host
     size_t stage_bytes[16] = {};
     std::mutex mu;
@@ -120,7 +123,7 @@ int check_tiles(const mb_tile *tiles, uint32_t n_tiles, uint32_t *max_w, uint32_
             return fail(MB_ERR_INVALID, "tile %u: rectangle exceeds the chunk grid", k);
         if (t.mrd > 0x7fffffffu) return fail(MB_ERR_INVALID, "tile %u: mrd exceeds int32 (.py:39)", k);
         if (t.out_pitch < t.w) return fail(MB_ERR_INVALID, "tile %u: out_pitch < w", k);
-        if (t.flags & ~(uint32_t)MB_TILE_PERIOD_SHORTCUT) return fail(MB_ERR_INVALID, "tile %u: unknown flag bits 0x%x", k, t.flags);
+        if (t.flags & ~(uint32_t)(MB_TILE_PERIOD_SHORTCUT | MB_TILE_LANE_REFILL)) return fail(MB_ERR_INVALID, "tile %u: unknown flag bits 0x%x", k, t.flags);
         if (t.flags != tiles[0].flags) return fail(MB_ERR_INVALID, "tile %u: every tile of one launch must carry the same flags", k);
         mw = t.w > mw ? t.w : mw;
         mh = t.h > mh ? t.h : mh;
@@ -138,6 +141,8 @@ int check_tiles(const mb_tile *tiles, uint32_t n_tiles, uint32_t *max_w, uint32_
 constexpr int kWX = 2, kWY = 2, kMinCtas = 12, kHead = 32;
 constexpr uint32_t kCtaW = kWX * mbk::kWarpW, kCtaH = kWY * mbk::kWarpH;
 constexpr uint32_t kMaxGridY = 65535;
+constexpr int kRefillCtas = 8;             // resident CTAs per SM of the lane-refill kernel (<= 64 registers; 8 warps per sub-partition saturate the FP64 pipe)
+constexpr uint32_t kCounterRing = 256;
 
 template <typename OutT>
 int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtype, cudaStream_t st)
@@ -195,6 +200,43 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
         return rc;
     }
 #endif
+    if (tiles[0].flags & MB_TILE_LANE_REFILL) {
+        // persistent warps: patches handed out by one atomic counter per launch (escape_refill.cuh)
+        cudaError_t e = cudaSuccess;
+        if (!c->counters) {
+            e = cudaMalloc((void **)&c->counters, sizeof(unsigned long long) * kCounterRing);
+            if (e != cudaSuccess) c->counters = nullptr;
+        }
+        if (e == cudaSuccess) {
+            args.counter = c->counters + (c->next_counter++ % kCounterRing);
+            e = cudaMemsetAsync(args.counter, 0, sizeof(unsigned long long), st);
+        }
+        if (e != cudaSuccess) {
+            rc = fail(MB_ERR_CUDA, "patch counter: %s", cudaGetErrorString(e));
+        } else {
+            args.dev = tiles_dev;
+            args.n_tiles = n_tiles;
+            args.pcols = (mw + mbk::kWarpW - 1) / mbk::kWarpW;
+            args.prows = (mh + mbk::kWarpH - 1) / mbk::kWarpH;
+            const unsigned long long slots = (unsigned long long)args.pcols * args.prows * n_tiles;
+            unsigned long long ctas = (slots + 3) / 4;
+            const unsigned long long cap = (unsigned long long)c->sm_count * kRefillCtas;
+            if (ctas > cap) ctas = cap;
+            const bool period = (tiles[0].flags & MB_TILE_PERIOD_SHORTCUT) != 0;
+            const dim3 grid((unsigned)ctas, 1, 1), block(128, 1, 1);
+            if (dtype == MB_DTYPE_F64) {
+                if (period) mbk::escape_refill_kernel<double, OutT, kRefillCtas, true><<<grid, block, 0, st>>>(args, out_dev);
+                else mbk::escape_refill_kernel<double, OutT, kRefillCtas, false><<<grid, block, 0, st>>>(args, out_dev);
+            } else {
+                if (period) mbk::escape_refill_kernel<float, OutT, kRefillCtas, true><<<grid, block, 0, st>>>(args, out_dev);
+                else mbk::escape_refill_kernel<float, OutT, kRefillCtas, false><<<grid, block, 0, st>>>(args, out_dev);
+            }
+            e = cudaGetLastError();
+            if (e != cudaSuccess) rc = fail(MB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+        }
+        if (tiles_dev) cudaFreeAsync(tiles_dev, st);
+        return rc;
+    }
     const uint64_t ctas64 = (uint64_t)((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
     cudaError_t err = cudaSuccess;
     if (ctas64 > 0x7fffffffull) {
@@ -296,6 +338,8 @@ void mb_shutdown(void)
         if (!c.ready) continue;
         cudaSetDevice(d);
         if (c.scratch) cudaFree(c.scratch);
+        if (c.counters) cudaFree(c.counters);
+        c.counters = nullptr;
         for (int k = 0; k < 16; ++k) { if (c.stage[k]) cudaFree(c.stage[k]); c.stage[k] = nullptr; c.stage_bytes[k] = 0; }
         if (c.stream) cudaStreamDestroy(c.stream);
         for (auto &ln : c.lanes) { if (ln) cudaStreamDestroy(ln); ln = nullptr; }
@@ -311,6 +355,14 @@ int mb_set_period_shortcut(int enabled)
 {
     const int was = (g_tile_flags & MB_TILE_PERIOD_SHORTCUT) ? 1 : 0;
     g_tile_flags = enabled ? (g_tile_flags | MB_TILE_PERIOD_SHORTCUT) : (g_tile_flags & ~(uint32_t)MB_TILE_PERIOD_SHORTCUT);
+    return was;
+}
+
+int mb_set_tile_flags(uint32_t flags)
+{
+    const int was = (int)g_tile_flags;
+    if (flags & ~(uint32_t)(MB_TILE_PERIOD_SHORTCUT | MB_TILE_LANE_REFILL)) return fail(MB_ERR_INVALID, "unknown flag bits 0x%x", flags);
+    g_tile_flags = flags;
     return was;
 }
 

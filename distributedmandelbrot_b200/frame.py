@@ -36,6 +36,7 @@ class FrameSpec:
     dtype: str = "f64"
     band_rows: int = 256          # rows per dispatch unit (a band is contiguous in the chunk layout)
     shortcut: bool = False        # MB_TILE_PERIOD_SHORTCUT on every band (bit-identical counts, fewer executed updates)
+    refill: bool = False          # MB_TILE_LANE_REFILL on every band (persistent warps; for the deep zooms)
 
     @property
     def n_chunks(self) -> int:
@@ -75,7 +76,7 @@ def frame_bands(spec: FrameSpec):
     d = spec.definition
     tiles, extents = [], []
     for c, (ir, ii) in enumerate(spec.chunk_indices()):
-        chunk = nat.chunk_geometry(spec.level, ir, ii, d, spec.mrd, shortcut=spec.shortcut)
+        chunk = nat.chunk_geometry(spec.level, ir, ii, d, spec.mrd, shortcut=spec.shortcut, refill=spec.refill)
         for y0 in range(0, d, spec.band_rows):
             h = min(spec.band_rows, d - y0)
             off = c * d * d + y0 * d
@@ -266,14 +267,14 @@ def queue_name() -> str:
 
 # ---- end-to-end in-box path: band-granular dispatch into ONE shared pinned host frame ----------------
 
-def workload_bands(workloads, definition: int, band_rows: int, shortcut: bool = False):
+def workload_bands(workloads, definition: int, band_rows: int, shortcut: bool = False, refill: bool = False):
     """Row-band tiles for a list of (level, mrd, index_real, index_imag) workloads.  Band k of chunk c
     is unit c * bands_per_chunk + k of the host frame; out_offset is its BYTE offset in the frame of
     uint8 payloads (chunk c's payload = bytes [c*d*d, (c+1)*d*d), exactly process_workload's output)."""
     d = int(definition)
     tiles = []
     for c, (level, mrd, ir, ii) in enumerate(workloads):
-        chunk = nat.chunk_geometry(level, ir, ii, d, mrd, shortcut=shortcut)
+        chunk = nat.chunk_geometry(level, ir, ii, d, mrd, shortcut=shortcut, refill=refill)
         for y0 in range(0, d, band_rows):
             h = min(band_rows, d - y0)
             tiles.append(chunk.sub(0, y0, d, h, c * d * d + y0 * d, d))
@@ -299,7 +300,7 @@ class InboxWorker:
     def __init__(self, workloads, definition: int = nat.CHUNK_DEFINITION, band_rows: int = 256, rank: int = 0,
                  world: int = 1, device: Optional[int] = None, name: Optional[str] = None, barrier: Optional[Callable] = None,
                  shortcut: bool = False, dtype: str = "f64", bands_per_claim: int = 4, depth: int = 6,
-                 launch: Optional[Callable] = None):
+                 launch: Optional[Callable] = None, refill: bool = False):
         self.workloads = [tuple(int(v) for v in w) for w in workloads]
         self.definition, self.band_rows = int(definition), int(band_rows)
         self.rank, self.world, self.dtype = rank, world, dtype
@@ -308,7 +309,7 @@ class InboxWorker:
         self._launch = launch
         if launch is None:
             nat.ensure_init(device)
-        self.tiles, self.bands_per_chunk = workload_bands(self.workloads, self.definition, self.band_rows, shortcut)
+        self.tiles, self.bands_per_chunk = workload_bands(self.workloads, self.definition, self.band_rows, shortcut, refill)
         self.n_bands = len(self.tiles)
         self.chunk_bytes = self.definition * self.definition
         name = name or queue_name()

@@ -84,7 +84,8 @@ def process_workload_counts(level: int, mrd: int, index_real: int, index_imag: i
     return out
 
 
-def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, depth: int = 4, shortcut: bool = False):
+def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, depth: int = 4, shortcut: bool = False,
+                      refill: bool = False):
     """Batch form of process_workload for a list of (level, mrd, index_real, index_imag).
 
     Same result per workload as process_workload (uint8[definition^2] in HOST memory), but the
@@ -95,7 +96,8 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
     `workloads` may be any iterable and is consumed lazily (e.g. a generator that pops chunk
     indices from the in-box work-stealing queue, or one that asks a Distributer for the next lease).
     shortcut=True renders with the exact orbit-periodicity shortcut (MB_TILE_PERIOD_SHORTCUT):
-    identical payloads, fewer executed updates inside the set.
+    identical payloads, fewer executed updates inside the set; refill=True uses the persistent-warp
+    kernel with lane refill (MB_TILE_LANE_REFILL, for deep zooms).
     """
     import itertools
     import torch
@@ -133,7 +135,7 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
         tiles = []
         for j, (level, mrd, ir, ii) in enumerate(batch):
             _check_u32(level=level, mrd=mrd, index_real=ir, index_imag=ii, definition=definition)
-            t = nat.chunk_geometry(level, ir, ii, definition, mrd, shortcut=shortcut)
+            t = nat.chunk_geometry(level, ir, ii, definition, mrd, shortcut=shortcut, refill=refill)
             t.out_offset = j * n
             tiles.append(t)
         slot = k % depth

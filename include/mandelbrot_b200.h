@@ -69,7 +69,7 @@ typedef struct mb_tile {
     uint32_t x0, y0, w, h;
     uint64_t out_offset;   /* in elements */
     uint32_t out_pitch;    /* elements between successive tile rows in out */
-    uint32_t flags;        /* 0, or MB_TILE_PERIOD_SHORTCUT; the same for every tile of one launch */
+    uint32_t flags;        /* 0 or MB_TILE_* bits below; the same for every tile of one launch */
 } mb_tile;                 /* 88 bytes */
 
 /*
@@ -82,6 +82,14 @@ typedef struct mb_tile {
  * numbers, which always count executed work.
  */
 #define MB_TILE_PERIOD_SHORTCUT 1u
+/*
+ * mb_tile.flags bit 1 -- persistent warps with lane refill (escape_refill.cuh): lanes that finish
+ * (escaped, out of updates, or on a cycle) are handed the next pixel instead of waiting for the
+ * slowest lane of their 8x4 patch.  Bit-identical counts.  Meant for deep zooms (escape counts in
+ * the hundreds or more): there is no tested head, a pixel that escapes after 3 updates pays a whole
+ * trip of 16.  May be combined with MB_TILE_PERIOD_SHORTCUT.
+ */
+#define MB_TILE_LANE_REFILL 2u
 
 /* ---- lifecycle ----------------------------------------------------------------------- */
 
@@ -100,6 +108,9 @@ int mb_sm_count(void);
  * Off by default.  Returns the previous setting.  Tile-array entry points take the flag per tile.
  */
 int mb_set_period_shortcut(int enabled);
+/* same switch for the whole flag word (MB_TILE_PERIOD_SHORTCUT | MB_TILE_LANE_REFILL); returns the
+ * previous flags, or MB_ERR_INVALID for unknown bits */
+int mb_set_tile_flags(uint32_t flags);
 /*
  * Diagnostic for shortcut launches of THIS thread: counter_dev (device uint64, caller-zeroed, NULL
  * to disable) accumulates the updates the kernel actually executed, to be set against
