@@ -7,12 +7,17 @@
 //     byte 0 = codec: 0x00 raw -> the n payload bytes ; 0x01 RLE -> (uint32 LE runLength, uint8
 //     value) records, one per maximal run.  Raw wins ties (`<` with Raw first, DataChunk.cs:188).
 //
-// Four small kernels; every pass is a coalesced 128-bit stream over the payload:
-//   1 count_run_starts   per-CTA number of run starts (p[i] != p[i-1], i = 0 always starts a run)
-//   2 scan_block_counts  exclusive scan of the CTA counts, picks the codec, writes header + length
-//   3 scatter_runs       RLE: every run start -> starts[r], value byte into its record
-//                        raw: the payload copied behind the header byte (byte-shifted words)
-//   4 write_run_lengths  RLE: runLength = starts[r+1] - starts[r] into the records
+// ONE pass over the payload for every chunk that ends up RLE (rle_single_pass): a tile of
+// kTile bytes per CTA, run starts found with SIMD byte compares, a decoupled look-back scan across
+// the chunk's tiles carrying (number of run starts, position of the last run start), complete
+// 5-byte records assembled in shared memory and written with 16-byte stores.  A record is emitted
+// by the CTA in whose tile the run ENDS -- there both its length (this start minus the previous
+// start, which the scan carries across tiles however long the run was) and its value (the byte
+// before the new start) are known, so no second pass and no look-ahead are needed; the chunk's last
+// run is closed by the last tile.  Records go straight to their final place; a tile stops emitting
+// once the runs before it already make RLE impossible (5 * runs >= n).  Only a chunk that ends up
+// Raw takes a second kernel (raw_fixup), which copies the payload behind the header byte.
+// Traffic: n read + serialised bytes written for RLE chunks (the algorithmic minimum).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -21,8 +26,11 @@
 namespace mbc {
 
 constexpr int kThreads = 256;
-constexpr int kBytesPerThread = 16;
-constexpr int kSegment = kThreads * kBytesPerThread;   // 4096 payload bytes per CTA
+constexpr int kHalf = 16;                              // one 128-bit load
+constexpr int kBytesPerThread = 2 * kHalf;             // two loads in flight per thread: 32 KiB per SM at 4 CTAs/SM
+constexpr int kTile = kThreads * kBytesPerThread;      // 8192 payload bytes per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kStageBytes = 5 * kTile + 32;            // worst case: every byte of the tile starts a run
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -35,19 +43,23 @@ struct Meta {
 };
 static_assert(sizeof(Meta) == 32, "mb_chunk_info layout");
 
+// look-back status of one tile: two self-validating 64-bit words (flag in the top two bits)
+struct TileStatus {
+    unsigned long long count;     // flag | run starts (aggregate of this tile, or inclusive prefix)
+    unsigned long long last;      // flag | 1 + position of the last run start (0 = none)
+};
+constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagInclusive = 2ull << 62, kFlagMask = 3ull << 62;
+
 // A batch of chunks is processed by one set of launches: blockIdx.y = chunk.
 struct Batch {
     const uint8_t *payloads;      // chunk c at payloads + c * payload_stride
     size_t payload_stride;
     uint8_t *out;                 // chunk c at out + c * out_stride (16-byte aligned stride)
     size_t out_stride;
-    uint32_t *counts;             // per chunk: counts + c * counts_stride
-    size_t counts_stride;
-    uint32_t *starts;             // per chunk: starts + c * starts_stride
-    size_t starts_stride;
+    TileStatus *status;           // per chunk: status + c * ntiles   (zeroed before every call)
     Meta *meta;                   // meta[c]
     size_t n;                     // payload bytes per chunk
-    uint32_t nblocks;             // CTAs per chunk
+    uint32_t ntiles;              // CTAs per chunk
 };
 
 // 4-bit mask of the bytes that differ between two words (SIMD byte compare, no per-byte loop)
@@ -57,14 +69,16 @@ __device__ __forceinline__ uint32_t differ4(uint32_t a, uint32_t b)
     return ((ne * 0x01020408u) >> 24) & 0xfu;                   // gather bits 0, 8, 16, 24 -> 0..3
 }
 
-// 16-bit mask: bit j set iff byte j of this thread's 16-byte span starts a run
-// (p[i] != p[i-1]; i = 0 always starts one).  `v` receives the 16 payload bytes (zero-padded).
-__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint4 &v)
+// 16-bit mask: bit j set iff byte j of the 16-byte span at `base` starts a run
+// (p[i] != p[i-1]; i = 0 always starts one).  `v` receives the 16 payload bytes (zero-padded),
+// `prev` the byte before the span.
+__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint4 &v, uint32_t &prev)
 {
     v = make_uint4(0, 0, 0, 0);
+    prev = 0;
     if (base >= n) return 0;
-    const uint32_t prev = base ? (uint32_t)p[base - 1] : 0u;
-    const bool full = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0);
+    prev = base ? (uint32_t)p[base - 1] : 0u;
+    const bool full = base + kHalf <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0);
     uint32_t mask;
     if (full) {
         v = *reinterpret_cast<const uint4 *>(p + base);
@@ -73,11 +87,11 @@ __device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, si
         const uint32_t s2 = __byte_perm(v.y, v.z, 0x6543), s3 = __byte_perm(v.z, v.w, 0x6543);
         mask = differ4(v.x, s0) | (differ4(v.y, s1) << 4) | (differ4(v.z, s2) << 8) | (differ4(v.w, s3) << 12);
     } else {
-        uint8_t bytes[kBytesPerThread];
+        uint8_t bytes[kHalf];
         mask = 0;
         uint8_t pb = (uint8_t)prev;
 #pragma unroll
-        for (int j = 0; j < kBytesPerThread; ++j) {
+        for (int j = 0; j < kHalf; ++j) {
             bytes[j] = (base + j < n) ? p[base + j] : 0;
             if (base + j < n && bytes[j] != pb) mask |= 1u << j;
             pb = bytes[j];
@@ -97,68 +111,183 @@ __device__ __forceinline__ uint32_t byte_of(const uint4 &v, int j)
     return (w >> (8 * (j & 3))) & 0xffu;
 }
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
+// byte j (0..31) of a thread's 32-byte span held in two 128-bit registers
+__device__ __forceinline__ uint32_t byte_of(const uint4 &v0, const uint4 &v1, int j)
 {
-    __shared__ uint32_t warp_sums[kThreads / 32];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
+    return j < kHalf ? byte_of(v0, j) : byte_of(v1, j - kHalf);
+}
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
+{
+    *reinterpret_cast<volatile unsigned long long *>(p) = v;
+}
+
+// The single pass.  grid = (ntiles, n_chunks), kThreads threads, kStageBytes of dynamic shared memory.
+// Tile ids follow blockIdx.x: blocks are dispatched in increasing linear index, so every
+// predecessor a tile waits for is running or done (the usual decoupled-look-back assumption).
+__global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
+{
+    extern __shared__ __align__(16) uint8_t stage[];
+    __shared__ uint32_t w_cnt[kWarps], w_last[kWarps];
+    __shared__ uint32_t s_runs_before, s_last_before;
+
+    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
+    uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
+    TileStatus *status = b.status + (size_t)blockIdx.y * b.ntiles;
+    const size_t n = b.n;
+    const uint32_t tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // 1. run starts of this thread's 32 bytes (two independent 128-bit loads)
+    uint4 v0, v1;
+    uint32_t prev, prev1;
+    const size_t base = (size_t)tile * kTile + (size_t)threadIdx.x * kBytesPerThread;
+    uint32_t mask = start_mask(p, base, n, v0, prev);
+    mask |= start_mask(p, base + kHalf, n, v1, prev1) << kHalf;
+    const uint32_t cnt = __popc(mask);
+    // 1 + position of my last start (0 = none); positions fit 32 bits (n < 2^32)
+    const uint32_t mylast = cnt ? (uint32_t)base + (31u - __clz(mask)) + 1u : 0u;
+
+    // 2. CTA-wide scan of (count, last start): inclusive in the warp, then across warps
+    uint32_t inc = cnt, lastinc = mylast;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (uint32_t)o) inc += t;
+        const uint32_t c = __shfl_up_sync(0xffffffffu, inc, o), l = __shfl_up_sync(0xffffffffu, lastinc, o);
+        if (lane >= (uint32_t)o) { inc += c; lastinc = lastinc > l ? lastinc : l; }
     }
-    if (lane == 31) warp_sums[warp] = inc;
+    if (lane == 31) { w_cnt[warp] = inc; w_last[warp] = lastinc; }
     __syncthreads();
-    uint32_t base = 0, tot = 0;
+    uint32_t wbase = 0, wlast = 0, tot = 0, totlast = 0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-        const uint32_t s = warp_sums[w];
-        if ((uint32_t)w < warp) base += s;
-        tot += s;
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = w_cnt[w], l = w_last[w];
+        if ((uint32_t)w < warp) { wbase += c; wlast = wlast > l ? wlast : l; }
+        tot += c;
+        totlast = totlast > l ? totlast : l;
+    }
+    const uint32_t rank = wbase + inc - cnt;                       // starts of this tile before my span
+    uint32_t lastex = __shfl_up_sync(0xffffffffu, lastinc, 1);     // last start before my span, inside the tile
+    if (lane == 0) lastex = 0;
+    lastex = lastex > wlast ? lastex : wlast;
+
+    // 3. decoupled look-back: (runs before this tile, last start before this tile)
+    if (warp == 0) {
+        unsigned long long runs_before = 0, last_before = 0;
+        if (tile == 0) {
+            if (lane == 0) {
+                st_status(&status[0].count, kFlagInclusive | tot);
+                st_status(&status[0].last, kFlagInclusive | totlast);
+            }
+        } else {
+            if (lane == 0) {
+                st_status(&status[tile].count, kFlagAggregate | tot);
+                st_status(&status[tile].last, kFlagAggregate | totlast);
+            }
+            int look = (int)tile - 1;                              // lane k inspects tile look - k
+            for (;;) {
+                const int t = look - (int)lane;
+                unsigned long long sc = kFlagInclusive, sl = kFlagInclusive;     // tiles "before 0": empty inclusive prefix
+                if (t >= 0) {
+                    do {
+                        sc = ld_status(&status[t].count);
+                        sl = ld_status(&status[t].last);
+                    } while ((sc & kFlagMask) == 0 || (sl & kFlagMask) == 0 || (sc & kFlagMask) != (sl & kFlagMask));
+                }
+                const bool inclusive = (sc & kFlagMask) == kFlagInclusive;
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, inclusive);
+                // use the window up to and including the nearest inclusive prefix
+                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
+                unsigned long long c = (int)lane <= stop ? (sc & ~kFlagMask) : 0ull;
+                unsigned long long l = (int)lane <= stop ? (sl & ~kFlagMask) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    c += __shfl_down_sync(0xffffffffu, c, o);
+                    const unsigned long long l2 = __shfl_down_sync(0xffffffffu, l, o);
+                    l = l > l2 ? l : l2;
+                }
+                c = __shfl_sync(0xffffffffu, c, 0);
+                l = __shfl_sync(0xffffffffu, l, 0);
+                runs_before += c;
+                last_before = last_before > l ? last_before : l;
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                const unsigned long long li = totlast ? (unsigned long long)totlast : last_before;
+                st_status(&status[tile].count, kFlagInclusive | (runs_before + tot));
+                st_status(&status[tile].last, kFlagInclusive | li);
+            }
+        }
+        if (lane == 0) { s_runs_before = (uint32_t)runs_before; s_last_before = (uint32_t)last_before; }
     }
     __syncthreads();
-    *total = tot;
-    return base + inc - v;
-}
+    const uint32_t runs_before = s_runs_before;
+    const bool is_last_tile = (tile + 1 == b.ntiles);
+    const uint32_t runs_total = runs_before + tot;                 // meaningful on the last tile
 
-__global__ void __launch_bounds__(kThreads) count_run_starts(const Batch b)
-{
-    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
-    uint32_t *__restrict__ block_counts = b.counts + blockIdx.y * b.counts_stride;
-    const size_t n = b.n;
-    uint4 v;
-    const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
-    const uint32_t c = __popc(start_mask(p, base, n, v));
-    uint32_t total;
-    block_exclusive_scan(c, &total);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
-}
-
-// one CTA per chunk; in-place exclusive scan of block_counts[0..nblocks)
-__global__ void __launch_bounds__(kThreads) scan_block_counts(const Batch b)
-{
-    uint32_t *__restrict__ block_counts = b.counts + blockIdx.x * b.counts_stride;
-    Meta *__restrict__ meta = b.meta + blockIdx.x;
-    uint8_t *__restrict__ out = b.out + blockIdx.x * b.out_stride;
-    const uint8_t *__restrict__ p = b.payloads + blockIdx.x * b.payload_stride;
-    const uint32_t nblocks = b.nblocks;
-    const size_t n = b.n;
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t first = 0; first < nblocks; first += kThreads) {
-        const uint32_t i = first + threadIdx.x;
-        const uint32_t v = i < nblocks ? block_counts[i] : 0;
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan(v, &total);
-        const uint32_t carry = carry_s;
-        if (i < nblocks) block_counts[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
+    // 4. records of the runs that END in this tile: run (g - 1) for every start with global index g >= 1,
+    //    plus the chunk's last run on the last tile.  Record r lives at out[1 + 5r .. 1 + 5r + 5).
+    //    Skipped when the runs before this tile already rule RLE out (5 * runs >= n keeps Raw).
+    const bool emit = (unsigned long long)runs_before * 5ull < (unsigned long long)n;
+    const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;           // first record this tile may write
+    uint32_t n_rec = tot - (runs_before ? 0u : (tot ? 1u : 0u));              // start 0 of the chunk closes nothing
+    if (is_last_tile) n_rec += 1u;
+    const size_t out_lo = 1 + (size_t)first_rec * 5;                          // byte range of this tile's records
+    const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_lo) & 15u);   // stage congruent to out mod 16
+    if (emit) {
+        uint32_t prevstart = lastex ? lastex - 1u : (s_last_before ? s_last_before - 1u : 0u);
+        uint32_t g = runs_before + rank;                                      // global index of my first start
+        while (mask) {                                                        // one trip per run start, not per byte
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t pos = (uint32_t)base + j;
+            if (g >= 1) {
+                const uint32_t len = pos - prevstart;                          // BitConverter.GetBytes(runLength): little-endian
+                const uint32_t val = j ? byte_of(v0, v1, j - 1) : prev;        // runValue = the byte before the new start
+                uint8_t *rec = stage + shift + (size_t)(g - 1 - first_rec) * 5;
+                rec[0] = (uint8_t)len;
+                rec[1] = (uint8_t)(len >> 8);
+                rec[2] = (uint8_t)(len >> 16);
+                rec[3] = (uint8_t)(len >> 24);
+                rec[4] = (uint8_t)val;
+            }
+            prevstart = pos;
+            ++g;
+        }
+        if (is_last_tile && threadIdx.x == 0) {
+            // the chunk's last run: from the last start anywhere to n
+            const uint32_t last_start = (totlast ? totlast : s_last_before) - 1u;
+            const uint32_t len = (uint32_t)n - last_start;
+            uint8_t *rec = stage + shift + (size_t)(runs_total - 1 - first_rec) * 5;
+            rec[0] = (uint8_t)len;
+            rec[1] = (uint8_t)(len >> 8);
+            rec[2] = (uint8_t)(len >> 16);
+            rec[3] = (uint8_t)(len >> 24);
+            rec[4] = p[n - 1];
+        }
     }
-    if (threadIdx.x == 0) {
-        const uint32_t runs = carry_s;
+    __syncthreads();
+    if (emit && n_rec) {
+        // copy out: bytes beyond n can never be part of an RLE result (5 * runs < n) and are dropped
+        size_t nbytes = (size_t)n_rec * 5;
+        if (out_lo + nbytes > n + 1) nbytes = out_lo < n + 1 ? n + 1 - out_lo : 0;
+        uint8_t *dst = out + out_lo;
+        const uint8_t *src = stage + shift;
+        const size_t head = nbytes < ((16u - shift) & 15u) ? nbytes : ((16u - shift) & 15u);
+        for (size_t k = threadIdx.x; k < head; k += kThreads) dst[k] = src[k];                 // up to the first 16-byte boundary
+        const size_t body = (nbytes - head) / 16;
+        for (size_t k = threadIdx.x; k < body; k += kThreads)
+            reinterpret_cast<uint4 *>(dst + head)[k] = reinterpret_cast<const uint4 *>(src + head)[k];
+        for (size_t k = head + body * 16 + threadIdx.x; k < nbytes; k += kThreads) dst[k] = src[k];
+    }
+
+    // 5. the last tile knows the run count: pick the codec, write header + length + classification
+    if (is_last_tile && threadIdx.x == 0) {
+        Meta *meta = b.meta + blockIdx.y;
+        const uint32_t runs = runs_total;
         // DataChunk.cs:181-204: the first serializer (Raw) is kept unless RLE is strictly shorter
         const bool rle = (unsigned long long)runs * 5ull < (unsigned long long)n;
         meta->runs = runs;
@@ -173,66 +302,38 @@ __global__ void __launch_bounds__(kThreads) scan_block_counts(const Batch b)
     }
 }
 
-__global__ void __launch_bounds__(kThreads) scatter_runs(const Batch b)
+// Second kernel, does work only for chunks that ended up Raw: RawSerializer
+// (DataChunkSerializer.cs:34-37), out[1 + i] = p[i].  The destination is 1 byte off alignment, so
+// aligned 16-byte words are built from two neighbouring source words.
+__global__ void __launch_bounds__(kThreads) raw_fixup(const Batch b)
 {
-    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
-    const uint32_t *__restrict__ block_offsets = b.counts + blockIdx.y * b.counts_stride;
     const Meta *__restrict__ meta = b.meta + blockIdx.y;
-    uint32_t *__restrict__ starts = b.starts + blockIdx.y * b.starts_stride;
+    if (meta->codec != 0) return;
+    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
     uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
     const size_t n = b.n;
-    uint4 v;
-    const size_t base = (size_t)blockIdx.x * kSegment + (size_t)threadIdx.x * kBytesPerThread;
-    if (meta->codec == 0) {
-        // RawSerializer (DataChunkSerializer.cs:34-37): out[1 + i] = p[i].  The destination is
-        // 1 byte off alignment, so build aligned 32-bit words from two neighbouring source words.
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        // 16-byte pieces, consecutive lanes on consecutive pieces (coalesced both ways)
+        const size_t base = (size_t)blockIdx.x * kTile + ((size_t)half * kThreads + threadIdx.x) * kHalf;
         if (base >= n) return;
-        const bool fast = base + kBytesPerThread <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
+        const bool fast = base + kHalf <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
                           ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
         if (fast) {
-            v = *reinterpret_cast<const uint4 *>(p + base);
-            const uint32_t before = base ? (uint32_t)p[base - 1] : (uint32_t)out[0];   // header byte for the very first word
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+            const uint32_t before = base ? (uint32_t)p[base - 1] : 0u;             // header byte (0x00 = raw) for the very first word
             uint4 w;
             w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
             w.y = __byte_perm(v.x, v.y, 0x6543);          // {v.x.b3, v.y.b0, v.y.b1, v.y.b2}
             w.z = __byte_perm(v.y, v.z, 0x6543);
             w.w = __byte_perm(v.z, v.w, 0x6543);
             *reinterpret_cast<uint4 *>(out + base) = w;   // covers out[base .. base+15] = {p[base-1], p[base .. base+14]}
-            if (base + kBytesPerThread == n) out[n] = (uint8_t)(v.w >> 24);           // last payload byte
+            if (base + kHalf == n) out[n] = (uint8_t)(v.w >> 24);                  // last payload byte
         } else {
             // a word-building neighbour to the left leaves out[base] (= p[base-1]) to this thread
             if (base) out[base] = p[base - 1];
-            for (int j = 0; j < kBytesPerThread && base + j < n; ++j) out[1 + base + j] = p[base + j];
+            for (int j = 0; j < kHalf && base + j < n; ++j) out[1 + base + j] = p[base + j];
         }
-        return;
-    }
-    uint32_t mask = start_mask(p, base, n, v);
-    uint32_t total;
-    uint32_t r = block_offsets[blockIdx.x] + block_exclusive_scan(__popc(mask), &total);
-    while (mask) {                                        // one trip per run start, not per byte
-        const int j = __ffs(mask) - 1;
-        mask &= mask - 1;
-        starts[r] = (uint32_t)(base + j);
-        out[1 + (size_t)r * 5 + 4] = (uint8_t)byte_of(v, j);   // runValue (DataChunkSerializer.cs:84,98)
-        ++r;
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) write_run_lengths(const Batch b)
-{
-    const Meta *__restrict__ meta = b.meta + blockIdx.y;
-    const uint32_t *__restrict__ starts = b.starts + blockIdx.y * b.starts_stride;
-    uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
-    const size_t n = b.n;
-    if (meta->codec == 0) return;
-    const uint32_t runs = meta->runs;
-    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < runs; r += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t len = (r + 1 < runs ? starts[r + 1] : (uint32_t)n) - starts[r];
-        uint8_t *rec = out + 1 + r * 5;                   // BitConverter.GetBytes(runLength): little-endian
-        rec[0] = (uint8_t)len;
-        rec[1] = (uint8_t)(len >> 8);
-        rec[2] = (uint8_t)(len >> 16);
-        rec[3] = (uint8_t)(len >> 24);
     }
 }
 

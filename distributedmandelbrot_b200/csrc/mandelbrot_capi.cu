@@ -879,17 +879,15 @@ int mb_frame_render_u8_host_units(const uint32_t *units, uint32_t n_units, const
 
 // ---- serialisation (f2) --------------------------------------------------------------------
 
-static size_t codec_blocks(size_t n) { return (n + mbc::kSegment - 1) / mbc::kSegment; }
+static size_t codec_tiles(size_t n) { return (n + mbc::kTile - 1) / mbc::kTile; }
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static size_t codec_counts_stride(size_t n) { return round_up(codec_blocks(n) + 1, 64); }
-static size_t codec_starts_stride(size_t n) { return round_up(n / 5 + 2, 64); }
 
 size_t mb_serialize_out_stride(size_t n) { return round_up(n + 1, 256); }
 
 size_t mb_serialize_workspace_bytes(size_t n, uint32_t n_chunks)
 {
-    // per chunk: block counts/offsets | run starts (RLE is only kept when 5 * runs < n)
-    return 256 + (size_t)n_chunks * sizeof(uint32_t) * (codec_counts_stride(n) + codec_starts_stride(n));
+    // per chunk: one 16-byte look-back status per 8 KiB tile
+    return 256 + (size_t)n_chunks * sizeof(mbc::TileStatus) * codec_tiles(n);
 }
 
 int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks, size_t payload_stride, uint8_t *out_dev,
@@ -901,6 +899,7 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     if (payload_stride < n) return fail(MB_ERR_INVALID, "payload_stride < n");
     if (out_stride < n + 1) return fail(MB_ERR_INVALID, "out_stride must be >= n + 1");
     if (workspace_bytes < mb_serialize_workspace_bytes(n, n_chunks)) return fail(MB_ERR_INVALID, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 15u) return fail(MB_ERR_INVALID, "workspace must be 16-byte aligned");
     static_assert(sizeof(mb_chunk_info) == sizeof(mbc::Meta), "mb_chunk_info mirrors mbc::Meta");
     DeviceCtx *c = nullptr;
     int rc = current_ctx(&c);
@@ -911,19 +910,15 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.payload_stride = payload_stride;
     b.out = out_dev;
     b.out_stride = out_stride;
-    b.counts = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(workspace_dev) + 256);
-    b.counts_stride = codec_counts_stride(n);
-    b.starts = b.counts + (size_t)n_chunks * b.counts_stride;
-    b.starts_stride = codec_starts_stride(n);
+    b.status = reinterpret_cast<mbc::TileStatus *>(static_cast<uint8_t *>(workspace_dev) + 256);
     b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
     b.n = n;
-    b.nblocks = (uint32_t)codec_blocks(n);
-    const dim3 per_chunk(b.nblocks, n_chunks, 1);
-    mbc::count_run_starts<<<per_chunk, mbc::kThreads, 0, st>>>(b);
-    mbc::scan_block_counts<<<n_chunks, mbc::kThreads, 0, st>>>(b);
-    mbc::scatter_runs<<<per_chunk, mbc::kThreads, 0, st>>>(b);
-    const dim3 len_grid((unsigned)grid_for(n / 5 + 1, c->sm_count), n_chunks, 1);
-    mbc::write_run_lengths<<<len_grid, mbc::kThreads, 0, st>>>(b);
+    b.ntiles = (uint32_t)codec_tiles(n);
+    // the look-back flags must start out invalid
+    MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.ntiles * sizeof(mbc::TileStatus), st));
+    const dim3 grid(b.ntiles, n_chunks, 1);
+    mbc::rle_single_pass<<<grid, mbc::kThreads, mbc::kStageBytes, st>>>(b);       // everything, for chunks that end up RLE
+    mbc::raw_fixup<<<grid, mbc::kThreads, 0, st>>>(b);                            // exits at once unless the chunk ended up Raw
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -77,14 +77,26 @@ def test_device_serializer_golden_and_shapes(gpu, codec, golden_meta, golden_arr
         payload = np.ascontiguousarray(golden_arrays[rec["key"] + "_payload"])
         assert _serialize_gpu(gpu, payload) == golden_arrays[rec["key"] + "_serialized"].tobytes(), rec
     rng = np.random.default_rng(3)
-    for n in [1, 2, 15, 16, 17, 31, 4095, 4096, 4097, 8192, 100_003, 1_000_000]:
-        for kind in ("runs", "noise", "const", "alt"):
+    # sizes around the 32-byte thread span and the 8 KiB tile of the single-pass kernel; run structures that
+    # straddle tiles (long runs), that make RLE impossible late / early, and that sit exactly on tile seams
+    for n in [1, 2, 15, 16, 17, 31, 32, 33, 4095, 4096, 4097, 8191, 8192, 8193, 16384, 16385, 24577, 100_003, 300_000, 1_000_000]:
+        for kind in ("runs", "noise", "const", "alt", "long", "dense_then_const", "const_then_noise", "seams"):
             if kind == "runs":
                 p = np.repeat(rng.integers(0, 4, n // 3 + 2).astype(np.uint8), rng.integers(1, 12, n // 3 + 2))[:n]
             elif kind == "noise":
                 p = rng.integers(0, 256, n).astype(np.uint8)
             elif kind == "const":
                 p = np.full(n, 1, np.uint8)
+            elif kind == "long":
+                p = np.repeat(rng.integers(0, 256, n // 9000 + 2).astype(np.uint8), rng.integers(1, 30000, n // 9000 + 2))[:n]
+                if p.size < n:
+                    p = np.concatenate([p, np.full(n - p.size, 9, np.uint8)])
+            elif kind == "dense_then_const":
+                p = np.concatenate([rng.integers(0, 256, n // 10).astype(np.uint8), np.full(n - n // 10, 3, np.uint8)])
+            elif kind == "const_then_noise":
+                p = np.concatenate([np.full(n // 2, 3, np.uint8), rng.integers(0, 256, n - n // 2).astype(np.uint8)])
+            elif kind == "seams":
+                p = (np.arange(n) // 8192 % 2).astype(np.uint8)              # every run starts exactly on a tile boundary
             else:
                 p = (np.arange(n) % 2).astype(np.uint8)
             p = np.ascontiguousarray(p)
