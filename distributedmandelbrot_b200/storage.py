@@ -120,7 +120,7 @@ assert INFO_DTYPE.itemsize == C.sizeof(nat.ChunkInfo)
 
 def render_serialized_batch(workloads, *, definition: int = nat.CHUNK_DEFINITION):
     """Render + classify + serialise a batch of (level, mrd, ir, ii) in ONE set of launches
-    (one escape-kernel launch over all chunks, four serializer launches over all chunks).
+    (one escape-kernel launch over all chunks, two serializer launches over all chunks).
     Returns (infos: structured numpy array, fetch(k) -> bytes of chunk k's serialised form)."""
     import torch
     dev = torch.device("cuda", nat.ensure_init())
@@ -152,24 +152,141 @@ def render_serialized_batch(workloads, *, definition: int = nat.CHUNK_DEFINITION
     return infos, fetch
 
 
+class BatchSerializer:
+    """Double-buffered render + classify + serialise pipeline for the storage writer.
+
+    `submit(workloads)` enqueues one escape-kernel launch and the serializer launches for a batch on
+    the compute stream and returns at once; `collect(ticket)` waits for that batch's 32-byte info
+    records, copies exactly the serialised bytes of every Regular chunk into page-locked host memory
+    on a copy stream and returns them.  With two slots, batch k+1 renders while batch k crosses
+    PCIe and is written to disk (DataStorage.WriteDataToFile, DataStorage.cs:333-350)."""
+
+    def __init__(self, definition: int, batch: int, slots: int = 2):
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda", nat.ensure_init())
+        self.lib = nat.lib()
+        self.definition, self.batch = int(definition), max(1, int(batch))
+        self.n = self.definition * self.definition
+        self.stride = self.lib.mb_serialize_out_stride(self.n)
+        self.wsb = self.lib.mb_serialize_workspace_bytes(self.n, self.batch)
+        nb = self.batch
+        self.slots = [{
+            "payload": torch.empty(nb * self.n, dtype=torch.uint8, device=self.dev),
+            "out": torch.empty(nb * self.stride, dtype=torch.uint8, device=self.dev),
+            "ws": torch.empty(self.wsb, dtype=torch.uint8, device=self.dev),
+            "info": torch.empty(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device=self.dev),
+            "info_host": torch.empty(nb * INFO_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+            "host": torch.empty(nb * self.stride, dtype=torch.uint8).pin_memory(),
+            "ready": None, "free": None,
+        } for _ in range(max(1, slots))]
+        self.compute = torch.cuda.Stream(self.dev)
+        self.copy = torch.cuda.Stream(self.dev)
+        self._next = 0
+
+    def submit(self, workloads):
+        torch = self.torch
+        workloads = list(workloads)
+        if not 0 < len(workloads) <= self.batch:
+            raise ValueError("batch size out of range")
+        slot = self.slots[self._next % len(self.slots)]
+        self._next += 1
+        if slot["free"] is not None:
+            slot["free"].synchronize()            # the slot's previous device->host copies are done
+        nb, n = len(workloads), self.n
+        tiles = []
+        for k, (level, mrd, ir, ii) in enumerate(workloads):
+            t = nat.chunk_geometry(level, ir, ii, self.definition, mrd)
+            t.out_offset = k * n
+            tiles.append(t)
+        st = self.compute.cuda_stream
+        nat.check(self.lib.mb_render_u8(nat.tile_array(tiles), nb, slot["payload"].data_ptr(), nat.DTYPE_F64, st))
+        nat.check(self.lib.mb_serialize_chunks(slot["payload"].data_ptr(), n, nb, n, slot["out"].data_ptr(), self.stride,
+                                               slot["ws"].data_ptr(), self.wsb, slot["info"].data_ptr(), st))
+        with torch.cuda.stream(self.compute):
+            slot["info_host"][:nb * INFO_DTYPE.itemsize].copy_(slot["info"][:nb * INFO_DTYPE.itemsize], non_blocking=True)
+        slot["ready"] = torch.cuda.Event()
+        slot["ready"].record(self.compute)
+        return slot, workloads
+
+    def collect(self, ticket):
+        """-> [(workload, entry_type, memoryview of the serialised bytes or None)], valid until the
+        slot is reused (two submits later)."""
+        torch = self.torch
+        slot, workloads = ticket
+        slot["ready"].synchronize()
+        infos = slot["info_host"].numpy()[:len(workloads) * INFO_DTYPE.itemsize].view(INFO_DTYPE)
+        self.copy.wait_event(slot["ready"])
+        with torch.cuda.stream(self.copy):
+            for k in range(len(workloads)):
+                if int(infos["entry_type"][k]) == ENTRY_REGULAR:
+                    lo, ln = k * self.stride, int(infos["out_len"][k])
+                    slot["host"][lo:lo + ln].copy_(slot["out"][lo:lo + ln], non_blocking=True)
+        slot["free"] = torch.cuda.Event()
+        slot["free"].record(self.copy)
+        slot["free"].synchronize()                # ONE wait per batch; the next batch is already rendering
+        host = slot["host"].numpy()
+        out = []
+        for k, w in enumerate(workloads):
+            et = int(infos["entry_type"][k])
+            lo, ln = k * self.stride, int(infos["out_len"][k])
+            out.append((w, et, memoryview(host)[lo:lo + ln] if et == ENTRY_REGULAR else None))
+        return out
+
+
 def render_level_to_store(store: DataStore, level: int, mrd: int, chunks=None, *, definition: int = nat.CHUNK_DEFINITION,
-                          skip_completed: bool = True, batch: int = 16) -> int:
+                          skip_completed: bool = True, batch: int = 16, serializer=None) -> int:
     """Render chunks of `level` (all level^2 of them unless `chunks` is given, e.g. an iterator
     that pops indices from the in-box work-stealing queue) straight into the store, `batch` chunks
     per set of launches.  Chunks the index already holds are skipped, like the Distributer's resume
-    (Distributer.cs:165-175)."""
+    (Distributer.cs:165-175).
+
+    `chunks` is consumed LAZILY, one batch at a time, and only after the previous batch has been
+    submitted: a rank that draws from the shared queue claims work as fast as it renders it, so the
+    queue (not a static split) balances the ranks.  Batches are double-buffered: while batch k's
+    serialised bytes cross PCIe and are written to disk, batch k+1 is already rendering.
+    `serializer` (submit/collect) is injectable for CPU tests."""
+    import itertools
     have = {(l, r, i) for (l, r, i, _t, _f) in store.completed()} if skip_completed else set()
     if chunks is None:
         # Distributer.TryGetNextNeededWorkload order (Distributer.cs:335-353): indexReal outer, indexImag inner
         chunks = ((ir, ii) for ir in range(level) for ii in range(level))
-    todo = [(ir, ii) for (ir, ii) in chunks if (level, ir, ii) not in have]
-    for first in range(0, len(todo), max(1, batch)):
-        part = todo[first:first + max(1, batch)]
-        infos, fetch = render_serialized_batch([(level, mrd, ir, ii) for (ir, ii) in part], definition=definition)
-        for k, (ir, ii) in enumerate(part):
-            etype = int(infos["entry_type"][k])
-            store.save(level, ir, ii, etype, fetch(k) if etype == ENTRY_REGULAR else None)
-    return len(todo)
+    it = iter(chunks)
+    ser = serializer if serializer is not None else BatchSerializer(definition, batch)
+    batch = max(1, batch)
+    done = 0
+
+    def next_batch():
+        part = []
+        while len(part) < batch:
+            got = list(itertools.islice(it, batch - len(part)))      # claims at most what this batch still needs
+            if not got:
+                break
+            part += [(level, mrd, ir, ii) for (ir, ii) in got if (level, ir, ii) not in have]
+        return part
+
+    def write(ticket):
+        nonlocal done
+        for (lv, _m, ir, ii), etype, blob in ser.collect(ticket):
+            store.save(lv, ir, ii, etype, blob)
+            done += 1
+
+    pending = None
+    while True:
+        part = next_batch()
+        ticket = ser.submit(part) if part else None
+        if pending is not None:
+            write(pending)                      # overlaps with the batch just submitted
+        pending = ticket
+        if ticket is None:
+            break
+    return done
+
+
+def queue_chunks(queue, rank: int, order, claim: int):
+    """Chunk indices for this rank, drawn lazily from the shared work-stealing queue, `claim` at a time."""
+    while (g := queue.pop(rank, claim)) is not None:
+        yield from order[g[0]:g[0] + g[1]]
 
 
 def parse_levels(text: str):
@@ -222,11 +339,9 @@ def main(argv=None) -> None:
             if rank != 0:
                 q = nat.TileQueue(qn)
 
-            def mine():
-                while (g := q.pop(rank, args.batch)) is not None:
-                    yield from order[g[0]:g[0] + g[1]]
-
-            n = render_level_to_store(store, level, mrd, mine(), definition=args.definition, batch=args.batch)
+            # small claims: a level's chunks differ in cost by orders of magnitude, and stealing can only move what is unclaimed
+            n = render_level_to_store(store, level, mrd, queue_chunks(q, rank, order, max(1, args.batch // 4)),
+                                      definition=args.definition, batch=args.batch)
             dist.barrier()
             q.close()
         print(f"[rank {rank}] level {level} mrd {mrd}: {n} chunk(s) written to {store.dir}", flush=True)

@@ -118,3 +118,78 @@ def test_two_rank_inbox_worker_with_a_dead_rank(tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_rank_main, args=(2, _free_port(), f"/mbi_test_{os.getpid()}", str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+# ---- storage writer: lazy, queue-driven dispatch across ranks (no GPU: stub serializer) -------------
+
+class _StubSerializer:
+    """Stands in for storage.BatchSerializer: 'renders' a chunk as a constant payload and serialises it
+    with the restated CPU codec; records when batches were submitted relative to queue claims."""
+
+    def __init__(self, log, delay=0.0):
+        self.log, self.delay = log, delay
+
+    def submit(self, workloads):
+        import time
+        self.log.append(("submit", list(workloads)))
+        time.sleep(self.delay)
+        return list(workloads)
+
+    def collect(self, ticket):
+        import chunk_codec
+        out = []
+        for (level, mrd, ir, ii) in ticket:
+            payload = np.full(64, (ir * 7 + ii) % 5, np.uint8)
+            et = chunk_codec.entry_type(payload)
+            out.append(((level, mrd, ir, ii), et, chunk_codec.serialize(payload) if et == 0 else None))
+        return out
+
+
+def _store_rank(rank, world, port, name, tmp):
+    import torch.distributed as dist
+    from distributedmandelbrot_b200 import _native as nat
+    from distributedmandelbrot_b200.storage import DataStore, queue_chunks, render_level_to_store
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    level = 6
+    order = [(ir, ii) for ir in range(level) for ii in range(level)]
+    q = nat.TileQueue(name, world, len(order), create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        q = nat.TileQueue(name)
+    store = DataStore(tmp)
+    log = []
+    claimed = []
+
+    def mine():
+        for c in queue_chunks(q, rank, order, 2):
+            claimed.append(c)
+            log.append(("claim", c))
+            yield c
+
+    n = render_level_to_store(store, level, 50, mine(), definition=8, batch=4,
+                              serializer=_StubSerializer(log, delay=0.02 if rank == 1 else 0.0))
+    # lazy: never more than one batch (4 chunks) claimed ahead of the batch being submitted
+    ahead = 0
+    for kind, what in log:
+        ahead = ahead + 1 if kind == "claim" else ahead - len(what)
+        assert ahead <= 4, "chunks were claimed before the previous batch was submitted"
+    counts = [None] * world
+    dist.all_gather_object(counts, (n, claimed))
+    dist.barrier()
+    if rank == 0:
+        assert sum(c[0] for c in counts) == len(order)
+        assert sorted(x for c in counts for x in c[1]) == sorted(order), "every chunk claimed exactly once"
+        assert counts[0][0] > counts[1][0], "the fast rank took more than the slow one (work stealing while rendering)"
+        done = DataStore(tmp).completed()
+        assert sorted((lv, r, i) for (lv, r, i, _t, _f) in done) == sorted((level, r, i) for r, i in order)
+        with open(os.path.join(tmp, "ok"), "w") as f:
+            f.write(str([c[0] for c in counts]))
+    q.close()
+    dist.destroy_process_group()
+
+
+def test_storage_writer_draws_chunks_lazily_from_the_queue(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_store_rank, args=(2, _free_port(), f"/mbs_test_{os.getpid()}", str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
