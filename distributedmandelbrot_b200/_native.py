@@ -122,6 +122,7 @@ SIGNATURES = {
     "mb_host_free": (_int, [_vp]),
     "mb_process_workload_u8": (_int, [_u32, _u32, _u32, _u32, _u32, _vp]),
     "mb_process_workload_counts": (_int, [_u32, _u32, _u32, _u32, _u32, _int, _vp]),
+    "mb_process_workloads_u8": (_int, [_vp, _u32, _u32, _vp, _sz]),
     "mb_wsq_create": (_int, [C.c_char_p, _u32, _u32, C.POINTER(_vp)]),
     "mb_wsq_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
     "mb_wsq_reset": (_int, [_vp, _u32]),
@@ -235,10 +236,13 @@ class PinnedPool:
     `take(n)` returns a fresh-looking, writable uint8 array of n bytes that the caller owns like
     any numpy array; when the array (and every view of it) is garbage-collected the page-locked
     block goes back to the pool instead of being freed, so steady-state calls neither allocate nor
-    pin memory.  At most `keep` idle blocks per size are retained."""
+    pin memory.  At most `keep` idle blocks per size are retained, and at most `max_bytes` are
+    page-locked and handed out at any time: a caller that hoards results (a whole level in a list)
+    gets ordinary pageable arrays beyond that instead of exhausting lockable memory."""
 
-    def __init__(self, alloc=None, free=None, keep: int = 4):
-        self._alloc, self._free, self._keep = alloc, free, keep
+    def __init__(self, alloc=None, free=None, keep: int = 4, max_bytes: int = 1 << 30):
+        self._alloc, self._free, self._keep, self._max = alloc, free, keep, max_bytes
+        self.outstanding = 0                     # page-locked bytes currently owned by callers
         self._idle = {}                          # nbytes -> [address, ...]
         self._lock = threading.RLock()           # re-entrant: _give_back may run from __del__ inside take() (cyclic GC)
         self.allocated = 0
@@ -259,6 +263,9 @@ class PinnedPool:
     def take(self, n: int):
         import numpy as np
         with self._lock:
+            if self.outstanding + n > self._max:
+                return np.empty(n, dtype=np.uint8)       # over the cap: pageable memory, still correct, slower copy
+            self.outstanding += n
             idle = self._idle.get(n)
             addr = idle.pop() if idle else None
         if addr is None:
@@ -271,6 +278,7 @@ class PinnedPool:
 
     def _give_back(self, n: int, addr: int) -> None:
         with self._lock:
+            self.outstanding -= n
             idle = self._idle.setdefault(n, [])
             if len(idle) < self._keep:
                 idle.append(addr)

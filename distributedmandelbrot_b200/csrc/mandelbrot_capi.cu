@@ -576,6 +576,66 @@ int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real
     return MB_OK;
 }
 
+// process_workload for a LIST of workloads (the loop of the reference worker, .py:178-184 +
+// :70-100, with the per-chunk host work removed): geometry in C, several small chunks per launch
+// (about `launch_bytes` of payload each), launches round-robin on the internal lanes, every launch
+// followed by its device->host copy straight to the chunk's place in host_out.  Returns when all
+// payloads have landed.  host_out should be page-locked (mb_host_alloc) for the copies to overlap.
+int mb_process_workloads_u8(const uint32_t *workloads, uint32_t n_workloads, uint32_t definition, uint8_t *host_out,
+                            size_t launch_bytes)
+{
+    if (!workloads || !host_out) return fail(MB_ERR_INVALID, "NULL buffer");
+    if (n_workloads == 0) return MB_OK;
+    if (definition == 0) return fail(MB_ERR_INVALID, "definition must be >= 1");
+    DeviceCtx *c = nullptr;
+    int rc = current_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = (size_t)definition * definition;
+    if (launch_bytes == 0) launch_bytes = (size_t)4 << 20;
+    uint32_t group = (uint32_t)(launch_bytes / n);
+    if (group == 0) group = 1;
+    if (group > 1024) group = 1024;
+    constexpr uint32_t kSlots = 4, kLanes = 4;
+    for (uint32_t k = 0; k < kSlots; ++k) {
+        if (c->stage_bytes[k] >= n * group) continue;
+        if (c->stage[k]) { MB_CUDA(cudaFree(c->stage[k])); c->stage[k] = nullptr; c->stage_bytes[k] = 0; }
+        MB_CUDA(cudaMalloc(&c->stage[k], n * group));
+        c->stage_bytes[k] = n * group;
+    }
+    EventSet evs;
+    if (evs.add(kSlots)) return fail(MB_ERR_CUDA, "cudaEventCreate failed");
+    std::vector<mb_tile> tiles(group);
+    uint32_t launches = 0;
+    int result = MB_OK;
+    for (uint32_t first = 0; first < n_workloads && result == MB_OK; first += group, ++launches) {
+        const uint32_t cnt = n_workloads - first < group ? n_workloads - first : group;
+        for (uint32_t j = 0; j < cnt && result == MB_OK; ++j) {
+            const uint32_t *w = workloads + 4 * (size_t)(first + j);          // level, mrd, indexReal, indexImag (DistributerWorkload.cs:9-29)
+            if (w[1] == 0) { result = fail(MB_ERR_INVALID, "workload %u: mrd == 0 divides by zero in the uint8 scaling (.py:96)", first + j); break; }
+            result = mb_chunk_geometry(w[0], w[2], w[3], definition, w[1], &tiles[j]);
+            tiles[j].out_offset = (uint64_t)j * n;
+            tiles[j].flags = g_tile_flags;
+        }
+        if (result) break;
+        const uint32_t slot = launches % kSlots;
+        if (launches >= kSlots) {                                             // the slot's previous copy must have left the buffer
+            cudaError_t e = cudaEventSynchronize(evs.ev[slot]);
+            if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e)); break; }
+        }
+        cudaStream_t lane = c->lanes[launches % kLanes];
+        if ((result = mb_render_u8(tiles.data(), cnt, static_cast<uint8_t *>(c->stage[slot]), MB_DTYPE_F64, lane))) break;
+        cudaError_t e = cudaMemcpyAsync(host_out + (size_t)first * n, c->stage[slot], (size_t)cnt * n, cudaMemcpyDeviceToHost, lane);
+        if (e == cudaSuccess) e = cudaEventRecord(evs.ev[slot], lane);
+        if (e != cudaSuccess) result = fail(MB_ERR_CUDA, "payload copy: %s", cudaGetErrorString(e));
+    }
+    for (uint32_t k = 0; k < kLanes; ++k) {
+        cudaError_t e = cudaStreamSynchronize(c->lanes[k]);
+        if (e != cudaSuccess && !result) result = fail(MB_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    }
+    return result;
+}
+
 // ---- peer-shared frame buffer (8e, alternative to the gather) ------------------------------------
 
 int mb_peer_alloc(size_t bytes, void **dev_ptr, void *handle_out)

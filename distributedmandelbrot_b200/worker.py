@@ -51,8 +51,10 @@ def process_workload(level: int, mrd: int, index_real: int, index_imag: int, *,
                      definition: int = DEFINITION, out: np.ndarray | None = None) -> np.ndarray:
     """(.py:70-100) one DataChunk -> uint8[definition*definition], row-major, p = row*d + col.
 
-    Synchronous; returns a fresh C-contiguous host array owned by the caller (or fills `out`,
-    e.g. a pinned buffer).  Raises ValueError for level == 0 / index >= level (the checks of the
+    Synchronous; returns a fresh C-contiguous host array owned by the caller (or fills `out`).
+    The array is page-locked memory from a recycling pool (the copy runs at PCIe speed and the
+    block returns to the pool when the array is dropped); once a caller holds more than 1 GiB of
+    such results, further ones come as ordinary pageable arrays.  Raises ValueError for level == 0 / index >= level (the checks of the
     DataChunk ctor, DataChunk.cs:99-106) and mrd == 0 (division by zero at .py:96).
     """
     nat.ensure_init()
@@ -70,6 +72,8 @@ def process_workload(level: int, mrd: int, index_real: int, index_imag: int, *,
 
 
 _PAYLOADS = nat.PinnedPool()
+_SMALL_CHUNK = 1 << 20        # chunks up to 1 MiB go through the native list loop (mb_process_workloads_u8)
+_SLAB_BYTES = 64 << 20        # ... in page-locked slabs of at most this many payload bytes
 
 
 def process_workload_counts(level: int, mrd: int, index_real: int, index_imag: int, *,
@@ -100,11 +104,38 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
     kernel with lane refill (MB_TILE_LANE_REFILL, for deep zooms).
     """
     import itertools
-    import torch
     dev_index = nat.ensure_init()
-    device = torch.device("cuda", dev_index)
     n = int(definition) * int(definition)
     results = [] if consume is None else None
+    if n <= _SMALL_CHUNK:
+        # small chunks (reduced definitions, e.g. the 256^2 tiles of BASELINE config 2): a frame lasts well
+        # under a millisecond, so the whole loop runs in native code (mb_process_workloads_u8): geometry,
+        # grouping into ~4 MiB launches and the pipelined device->host copies, one call per slab
+        it = iter(workloads)
+        cap = max(1, min(4096, _SLAB_BYTES // n))
+        flags = (nat.TILE_PERIOD_SHORTCUT if shortcut else 0) | (nat.TILE_LANE_REFILL if refill else 0)
+        while True:
+            batch = list(itertools.islice(it, cap))
+            if not batch:
+                return results
+            for (level, mrd, ir, ii) in batch:
+                _check_u32(level=level, mrd=mrd, index_real=ir, index_imag=ii, definition=definition)
+            rec = np.asarray(batch, dtype=np.uint32).reshape(-1, 4)
+            slab = _PAYLOADS.take(len(batch) * n)
+            prev = nat.set_tile_flags(flags)
+            try:
+                nat.check(nat.lib().mb_process_workloads_u8(rec.ctypes.data_as(C.c_void_p), len(batch), int(definition),
+                                                            slab.ctypes.data_as(C.c_void_p), 0))
+            finally:
+                nat.set_tile_flags(prev)
+            for j, w in enumerate(batch):
+                payload = slab[j * n:(j + 1) * n]
+                if consume is None:
+                    results.append(payload.copy())
+                else:
+                    consume(w, payload)
+    import torch
+    device = torch.device("cuda", dev_index)
     depth = max(2, int(depth))
     # small chunks (reduced definitions) are grouped so that one launch and one copy carry ~4 MiB;
     # the reference's 4096^2 chunks (16 MiB) travel one per launch

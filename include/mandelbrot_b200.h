@@ -243,6 +243,17 @@ int mb_host_free(void *host_ptr);
 int mb_process_workload_u8(uint32_t level, uint32_t mrd, uint32_t index_real,
                            uint32_t index_imag, uint32_t definition, uint8_t *host_out);
 
+/*
+ * The worker loop's compute for a LIST of workloads in one call (.py:178-184 calling .py:70-100):
+ * workloads = n_workloads records of 4 uint32 (level, mrd, indexReal, indexImag -- the wire order,
+ * DistributerWorkload.cs:53-77); chunk k's payload lands at host_out + k * definition^2.  Small
+ * chunks are grouped into launches of about launch_bytes (0 = 4 MiB) of payload, launches and their
+ * device->host copies are pipelined internally; synchronous as a whole.  host_out: page-locked
+ * memory (mb_host_alloc) lets the copies overlap the kernels.  Honours mb_set_tile_flags.
+ */
+int mb_process_workloads_u8(const uint32_t *workloads, uint32_t n_workloads, uint32_t definition,
+                            uint8_t *host_out, size_t launch_bytes);
+
 /* same, int32 counts (what calc_mb_value returns before .py:96), definition^2 * 4 bytes */
 int mb_process_workload_counts(uint32_t level, uint32_t mrd, uint32_t index_real,
                                uint32_t index_imag, uint32_t definition, int dtype,

@@ -178,3 +178,12 @@ def test_pinned_pool_recycles_blocks(native):
     assert len(freed) == 3                    # keep = 2 idle blocks of a size, the rest is freed
     del b, c
     gc.collect()
+    assert pool.outstanding == 0
+    # a caller that hoards results is cut off from page-locked memory at max_bytes, not from results
+    small = native.PinnedPool(alloc=lambda n: libc.malloc(n), free=lambda a: libc.free(a), keep=1, max_bytes=2500)
+    hoard = [small.take(1000) for _ in range(4)]
+    assert small.allocated == 2 and small.outstanding == 2000           # the 3rd and 4th are pageable numpy arrays
+    assert all(h.shape == (1000,) and h.dtype == np.uint8 for h in hoard)
+    del hoard
+    gc.collect()
+    assert small.outstanding == 0
