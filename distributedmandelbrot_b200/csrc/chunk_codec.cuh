@@ -7,10 +7,10 @@
 //     byte 0 = codec: 0x00 raw -> the n payload bytes ; 0x01 RLE -> (uint32 LE runLength, uint8
 //     value) records, one per maximal run.  Raw wins ties (`<` with Raw first, DataChunk.cs:188).
 //
-// ONE pass over the payload for every chunk that ends up RLE (rle_single_pass): a tile of
-// kTile bytes per CTA, run starts found with SIMD byte compares, a decoupled look-back scan across
-// the chunk's tiles carrying (number of run starts, position of the last run start), complete
-// 5-byte records assembled in shared memory and written with 16-byte stores.  A record is emitted
+// ONE pass over HBM for every chunk that ends up RLE (rle_single_pass): run starts found with SIMD
+// byte compares, a decoupled look-back scan across the chunk's segments carrying (number of run
+// starts, position of the last run start), complete 5-byte records assembled in shared memory and
+// written with 16-byte stores.  A record is emitted
 // by the CTA in whose tile the run ENDS -- there both its length (this start minus the previous
 // start, which the scan carries across tiles however long the run was) and its value (the byte
 // before the new start) are known, so no second pass and no look-ahead are needed; the chunk's last
@@ -56,10 +56,12 @@ struct Batch {
     size_t payload_stride;
     uint8_t *out;                 // chunk c at out + c * out_stride (16-byte aligned stride)
     size_t out_stride;
-    TileStatus *status;           // per chunk: status + c * ntiles   (zeroed before every call)
+    TileStatus *status;           // per chunk: status + c * nsegs   (zeroed before every call)
     Meta *meta;                   // meta[c]
     size_t n;                     // payload bytes per chunk
-    uint32_t ntiles;              // CTAs per chunk
+    uint32_t ntiles;              // 8 KiB tiles per chunk
+    uint32_t seg_tiles;           // tiles per segment (one CTA of rle_single_pass)
+    uint32_t nsegs;               // segments per chunk
 };
 
 // 4-bit mask of the bytes that differ between two words (SIMD byte compare, no per-byte loop)
@@ -126,9 +128,37 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
 }
 
-// The single pass.  grid = (ntiles, n_chunks), kThreads threads, kStageBytes of dynamic shared memory.
-// Tile ids follow blockIdx.x: blocks are dispatched in increasing linear index, so every
-// predecessor a tile waits for is running or done (the usual decoupled-look-back assumption).
+// CTA-wide (sum, max) of a per-thread pair; every thread receives the totals
+__device__ __forceinline__ void block_sum_max(uint32_t c, uint32_t l, uint32_t *w_cnt, uint32_t *w_last, uint32_t &tot, uint32_t &totlast)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        const uint32_t l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        l = l > l2 ? l : l2;
+    }
+    __syncthreads();                       // the arrays may still be read by the previous user
+    if (lane == 0) { w_cnt[warp] = c; w_last[warp] = l; }
+    __syncthreads();
+    tot = 0;
+    totlast = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        tot += w_cnt[w];
+        totlast = totlast > w_last[w] ? totlast : w_last[w];
+    }
+}
+
+// The single pass.  grid = (segments, n_chunks), kThreads threads, kStageBytes of dynamic shared memory.
+// A CTA owns a SEGMENT of b.seg_tiles consecutive 8 KiB tiles:
+//   phase 1  streams the segment once from HBM and counts its run starts (+ position of the last one);
+//   look-back  one decoupled look-back per SEGMENT (a few hundred per chunk, not thousands of tiles:
+//            the chain is short and several chunks are in flight at once);
+//   phase 2  walks the segment's tiles again -- now L2 hits, the segment was just read -- and emits the
+//            records, carrying the running (runs, last start) in shared memory from tile to tile.
+// Segment ids follow blockIdx.x: blocks are dispatched in increasing linear index, so every
+// predecessor a segment waits for is running or done (the usual decoupled-look-back assumption).
 __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
 {
     extern __shared__ __align__(16) uint8_t stage[];
@@ -137,64 +167,48 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
 
     const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
     uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
-    TileStatus *status = b.status + (size_t)blockIdx.y * b.ntiles;
+    TileStatus *status = b.status + (size_t)blockIdx.y * b.nsegs;
     const size_t n = b.n;
-    const uint32_t tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile0 = seg * b.seg_tiles;
+    const uint32_t ntl = b.ntiles - tile0 < b.seg_tiles ? b.ntiles - tile0 : b.seg_tiles;
 
-    // 1. run starts of this thread's 32 bytes (two independent 128-bit loads)
-    uint4 v0, v1;
-    uint32_t prev, prev1;
-    const size_t base = (size_t)tile * kTile + (size_t)threadIdx.x * kBytesPerThread;
-    uint32_t mask = start_mask(p, base, n, v0, prev);
-    mask |= start_mask(p, base + kHalf, n, v1, prev1) << kHalf;
-    const uint32_t cnt = __popc(mask);
-    // 1 + position of my last start (0 = none); positions fit 32 bits (n < 2^32)
-    const uint32_t mylast = cnt ? (uint32_t)base + (31u - __clz(mask)) + 1u : 0u;
-
-    // 2. CTA-wide scan of (count, last start): inclusive in the warp, then across warps
-    uint32_t inc = cnt, lastinc = mylast;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t c = __shfl_up_sync(0xffffffffu, inc, o), l = __shfl_up_sync(0xffffffffu, lastinc, o);
-        if (lane >= (uint32_t)o) { inc += c; lastinc = lastinc > l ? lastinc : l; }
+    // ---- phase 1: run starts of the whole segment --------------------------------------------------
+    uint32_t seg_cnt = 0, seg_last = 0;
+    for (uint32_t k = 0; k < ntl; ++k) {
+        uint4 v0, v1;
+        uint32_t pv0, pv1;
+        const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
+        uint32_t m = start_mask(p, base, n, v0, pv0);
+        m |= start_mask(p, base + kHalf, n, v1, pv1) << kHalf;
+        seg_cnt += __popc(m);
+        if (m) seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;           // positions grow with k
     }
-    if (lane == 31) { w_cnt[warp] = inc; w_last[warp] = lastinc; }
-    __syncthreads();
-    uint32_t wbase = 0, wlast = 0, tot = 0, totlast = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        const uint32_t c = w_cnt[w], l = w_last[w];
-        if ((uint32_t)w < warp) { wbase += c; wlast = wlast > l ? wlast : l; }
-        tot += c;
-        totlast = totlast > l ? totlast : l;
-    }
-    const uint32_t rank = wbase + inc - cnt;                       // starts of this tile before my span
-    uint32_t lastex = __shfl_up_sync(0xffffffffu, lastinc, 1);     // last start before my span, inside the tile
-    if (lane == 0) lastex = 0;
-    lastex = lastex > wlast ? lastex : wlast;
+    uint32_t seg_tot, seg_totlast;
+    block_sum_max(seg_cnt, seg_last, w_cnt, w_last, seg_tot, seg_totlast);
 
-    // 3. decoupled look-back: (runs before this tile, last start before this tile)
+    // ---- decoupled look-back over segments: (runs before this segment, last start before it) -------
     if (warp == 0) {
         unsigned long long runs_before = 0, last_before = 0;
-        if (tile == 0) {
+        if (seg == 0) {
             if (lane == 0) {
-                st_status(&status[0].count, kFlagInclusive | tot);
-                st_status(&status[0].last, kFlagInclusive | totlast);
+                st_status(&status[0].count, kFlagInclusive | seg_tot);
+                st_status(&status[0].last, kFlagInclusive | seg_totlast);
             }
         } else {
             if (lane == 0) {
-                st_status(&status[tile].count, kFlagAggregate | tot);
-                st_status(&status[tile].last, kFlagAggregate | totlast);
+                st_status(&status[seg].count, kFlagAggregate | seg_tot);
+                st_status(&status[seg].last, kFlagAggregate | seg_totlast);
             }
-            int look = (int)tile - 1;                              // lane k inspects tile look - k
+            int look = (int)seg - 1;                               // lane k inspects segment look - k
             for (;;) {
                 const int t = look - (int)lane;
-                unsigned long long sc = kFlagInclusive, sl = kFlagInclusive;     // tiles "before 0": empty inclusive prefix
+                unsigned long long sc = kFlagInclusive, sl = kFlagInclusive;     // "before segment 0": empty inclusive prefix
                 if (t >= 0) {
                     do {
                         sc = ld_status(&status[t].count);
                         sl = ld_status(&status[t].last);
-                    } while ((sc & kFlagMask) == 0 || (sl & kFlagMask) == 0 || (sc & kFlagMask) != (sl & kFlagMask));
+                    } while ((sc & kFlagMask) == 0 || (sc & kFlagMask) != (sl & kFlagMask));
                 }
                 const bool inclusive = (sc & kFlagMask) == kFlagInclusive;
                 const unsigned incl_mask = __ballot_sync(0xffffffffu, inclusive);
@@ -216,76 +230,116 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
                 look -= 32;
             }
             if (lane == 0) {
-                const unsigned long long li = totlast ? (unsigned long long)totlast : last_before;
-                st_status(&status[tile].count, kFlagInclusive | (runs_before + tot));
-                st_status(&status[tile].last, kFlagInclusive | li);
+                const unsigned long long li = seg_totlast ? (unsigned long long)seg_totlast : last_before;
+                st_status(&status[seg].count, kFlagInclusive | (runs_before + seg_tot));
+                st_status(&status[seg].last, kFlagInclusive | li);
             }
         }
         if (lane == 0) { s_runs_before = (uint32_t)runs_before; s_last_before = (uint32_t)last_before; }
     }
     __syncthreads();
-    const uint32_t runs_before = s_runs_before;
-    const bool is_last_tile = (tile + 1 == b.ntiles);
-    const uint32_t runs_total = runs_before + tot;                 // meaningful on the last tile
+    const bool last_seg = (seg + 1 == b.nsegs);
+    const uint32_t runs_total = s_runs_before + seg_tot;           // the chunk's run count, on the last segment
 
-    // 4. records of the runs that END in this tile: run (g - 1) for every start with global index g >= 1,
-    //    plus the chunk's last run on the last tile.  Record r lives at out[1 + 5r .. 1 + 5r + 5).
-    //    Skipped when the runs before this tile already rule RLE out (5 * runs >= n keeps Raw).
-    const bool emit = (unsigned long long)runs_before * 5ull < (unsigned long long)n;
-    const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;           // first record this tile may write
-    uint32_t n_rec = tot - (runs_before ? 0u : (tot ? 1u : 0u));              // start 0 of the chunk closes nothing
-    if (is_last_tile) n_rec += 1u;
-    const size_t out_lo = 1 + (size_t)first_rec * 5;                          // byte range of this tile's records
-    const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_lo) & 15u);   // stage congruent to out mod 16
-    if (emit) {
-        uint32_t prevstart = lastex ? lastex - 1u : (s_last_before ? s_last_before - 1u : 0u);
-        uint32_t g = runs_before + rank;                                      // global index of my first start
-        while (mask) {                                                        // one trip per run start, not per byte
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t pos = (uint32_t)base + j;
-            if (g >= 1) {
-                const uint32_t len = pos - prevstart;                          // BitConverter.GetBytes(runLength): little-endian
-                const uint32_t val = j ? byte_of(v0, v1, j - 1) : prev;        // runValue = the byte before the new start
-                uint8_t *rec = stage + shift + (size_t)(g - 1 - first_rec) * 5;
+    // ---- phase 2: records of the runs that END in each tile of the segment -------------------------
+    // run (g - 1) for every start with global index g >= 1, plus the chunk's last run on its last tile.
+    // Record r lives at out[1 + 5r .. 1 + 5r + 5).  Tiles from which on RLE is already ruled out
+    // (5 * runs >= n keeps Raw, and runs only grow) are skipped.
+    for (uint32_t k = 0; k < ntl; ++k) {
+        const uint32_t runs_before = s_runs_before, last_before = s_last_before;
+        if ((unsigned long long)runs_before * 5ull >= (unsigned long long)n) break;
+        const uint32_t tile = tile0 + k;
+        const bool is_last_tile = (tile + 1 == b.ntiles);
+        uint4 v0, v1;
+        uint32_t prev, prev1;
+        const size_t base = (size_t)tile * kTile + (size_t)threadIdx.x * kBytesPerThread;
+        uint32_t mask = start_mask(p, base, n, v0, prev);                       // L2 hits: phase 1 just read these lines
+        mask |= start_mask(p, base + kHalf, n, v1, prev1) << kHalf;
+        const uint32_t cnt = __popc(mask);
+        const uint32_t mylast = cnt ? (uint32_t)base + (31u - __clz(mask)) + 1u : 0u;
+        // CTA-wide scan of (count, last start): inclusive in the warp, then across warps
+        uint32_t inc = cnt, lastinc = mylast;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t c = __shfl_up_sync(0xffffffffu, inc, o), l = __shfl_up_sync(0xffffffffu, lastinc, o);
+            if (lane >= (uint32_t)o) { inc += c; lastinc = lastinc > l ? lastinc : l; }
+        }
+        __syncthreads();                                                         // previous tile: staging copied out, w_* consumed
+        if (lane == 31) { w_cnt[warp] = inc; w_last[warp] = lastinc; }
+        __syncthreads();
+        uint32_t wbase = 0, wlast = 0, tot = 0, totlast = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = w_cnt[w], l = w_last[w];
+            if ((uint32_t)w < warp) { wbase += c; wlast = wlast > l ? wlast : l; }
+            tot += c;
+            totlast = totlast > l ? totlast : l;
+        }
+        const uint32_t rank = wbase + inc - cnt;                       // starts of this tile before my span
+        uint32_t lastex = __shfl_up_sync(0xffffffffu, lastinc, 1);     // last start before my span, inside the tile
+        if (lane == 0) lastex = 0;
+        lastex = lastex > wlast ? lastex : wlast;
+
+        const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;           // first record this tile may write
+        uint32_t n_rec = tot - (runs_before ? 0u : (tot ? 1u : 0u));              // start 0 of the chunk closes nothing
+        if (is_last_tile) n_rec += 1u;
+        const size_t out_lo = 1 + (size_t)first_rec * 5;                          // byte range of this tile's records
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_lo) & 15u);   // stage congruent to out mod 16
+        {
+            uint32_t prevstart = lastex ? lastex - 1u : (last_before ? last_before - 1u : 0u);
+            uint32_t g = runs_before + rank;                                      // global index of my first start
+            while (mask) {                                                        // one trip per run start, not per byte
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t pos = (uint32_t)base + j;
+                if (g >= 1) {
+                    const uint32_t len = pos - prevstart;                          // BitConverter.GetBytes(runLength): little-endian
+                    const uint32_t val = j ? byte_of(v0, v1, j - 1) : prev;        // runValue = the byte before the new start
+                    uint8_t *rec = stage + shift + (size_t)(g - 1 - first_rec) * 5;
+                    rec[0] = (uint8_t)len;
+                    rec[1] = (uint8_t)(len >> 8);
+                    rec[2] = (uint8_t)(len >> 16);
+                    rec[3] = (uint8_t)(len >> 24);
+                    rec[4] = (uint8_t)val;
+                }
+                prevstart = pos;
+                ++g;
+            }
+            if (is_last_tile && threadIdx.x == 0) {
+                // the chunk's last run: from the last start anywhere to n
+                const uint32_t last_start = (totlast ? totlast : last_before) - 1u;
+                const uint32_t len = (uint32_t)n - last_start;
+                uint8_t *rec = stage + shift + (size_t)(runs_before + tot - 1 - first_rec) * 5;
                 rec[0] = (uint8_t)len;
                 rec[1] = (uint8_t)(len >> 8);
                 rec[2] = (uint8_t)(len >> 16);
                 rec[3] = (uint8_t)(len >> 24);
-                rec[4] = (uint8_t)val;
+                rec[4] = p[n - 1];
             }
-            prevstart = pos;
-            ++g;
         }
-        if (is_last_tile && threadIdx.x == 0) {
-            // the chunk's last run: from the last start anywhere to n
-            const uint32_t last_start = (totlast ? totlast : s_last_before) - 1u;
-            const uint32_t len = (uint32_t)n - last_start;
-            uint8_t *rec = stage + shift + (size_t)(runs_total - 1 - first_rec) * 5;
-            rec[0] = (uint8_t)len;
-            rec[1] = (uint8_t)(len >> 8);
-            rec[2] = (uint8_t)(len >> 16);
-            rec[3] = (uint8_t)(len >> 24);
-            rec[4] = p[n - 1];
+        __syncthreads();
+        if (n_rec) {
+            // copy out: bytes beyond n can never be part of an RLE result (5 * runs < n) and are dropped
+            size_t nbytes = (size_t)n_rec * 5;
+            if (out_lo + nbytes > n + 1) nbytes = out_lo < n + 1 ? n + 1 - out_lo : 0;
+            uint8_t *dst = out + out_lo;
+            const uint8_t *src = stage + shift;
+            const size_t head = nbytes < ((16u - shift) & 15u) ? nbytes : ((16u - shift) & 15u);
+            for (size_t q = threadIdx.x; q < head; q += kThreads) dst[q] = src[q];                 // up to the first 16-byte boundary
+            const size_t body = (nbytes - head) / 16;
+            for (size_t q = threadIdx.x; q < body; q += kThreads)
+                reinterpret_cast<uint4 *>(dst + head)[q] = reinterpret_cast<const uint4 *>(src + head)[q];
+            for (size_t q = head + body * 16 + threadIdx.x; q < nbytes; q += kThreads) dst[q] = src[q];
         }
-    }
-    __syncthreads();
-    if (emit && n_rec) {
-        // copy out: bytes beyond n can never be part of an RLE result (5 * runs < n) and are dropped
-        size_t nbytes = (size_t)n_rec * 5;
-        if (out_lo + nbytes > n + 1) nbytes = out_lo < n + 1 ? n + 1 - out_lo : 0;
-        uint8_t *dst = out + out_lo;
-        const uint8_t *src = stage + shift;
-        const size_t head = nbytes < ((16u - shift) & 15u) ? nbytes : ((16u - shift) & 15u);
-        for (size_t k = threadIdx.x; k < head; k += kThreads) dst[k] = src[k];                 // up to the first 16-byte boundary
-        const size_t body = (nbytes - head) / 16;
-        for (size_t k = threadIdx.x; k < body; k += kThreads)
-            reinterpret_cast<uint4 *>(dst + head)[k] = reinterpret_cast<const uint4 *>(src + head)[k];
-        for (size_t k = head + body * 16 + threadIdx.x; k < nbytes; k += kThreads) dst[k] = src[k];
+        if (threadIdx.x == 0) {                                                    // carry the prefix to the next tile
+            s_runs_before = runs_before + tot;
+            if (totlast) s_last_before = totlast;
+        }
+        __syncthreads();
     }
 
-    // 5. the last tile knows the run count: pick the codec, write header + length + classification
-    if (is_last_tile && threadIdx.x == 0) {
+    // the last segment knows the run count: pick the codec, write header + length + classification
+    if (last_seg && threadIdx.x == 0) {
         Meta *meta = b.meta + blockIdx.y;
         const uint32_t runs = runs_total;
         // DataChunk.cs:181-204: the first serializer (Raw) is kept unless RLE is strictly shorter

@@ -175,7 +175,7 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
                 bool periodic = false;
                 if constexpr (PERIOD) {
                     periodic = O::same_bits(ex, sx) && O::same_bits(ey, sy);
-                    if ((n & (n - 1)) == 0) { sx = ex; sy = ey; }
+                    if (save_point(n)) { sx = ex; sy = ey; }
                 }
                 const int left = lim - n;
                 if (periodic) {
@@ -245,7 +245,7 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
             continue;
         }
         n += 2 * K;
-        if constexpr (PERIOD) { if ((n & (n - 1)) == 0) { sx = bx; sy = by; } }
+        if constexpr (PERIOD) { if (save_point(n)) { sx = bx; sy = by; } }
         // ---- trip 2: b -> a -> (x, y)
         ax = bx; ay = by; axx = bxx; ayy = byy;
 #pragma unroll
@@ -264,7 +264,7 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
             continue;
         }
         n += 2 * K;
-        if constexpr (PERIOD) { if ((n & (n - 1)) == 0) { sx = x; sy = y; } }
+        if constexpr (PERIOD) { if (save_point(n)) { sx = x; sy = y; } }
     }
 
     if constexpr (PERIOD) {

@@ -946,7 +946,7 @@ size_t mb_serialize_out_stride(size_t n) { return round_up(n + 1, 256); }
 
 size_t mb_serialize_workspace_bytes(size_t n, uint32_t n_chunks)
 {
-    // per chunk: one 16-byte look-back status per 8 KiB tile
+    // per chunk: one 16-byte look-back status per segment (at most one per 8 KiB tile)
     return 256 + (size_t)n_chunks * sizeof(mbc::TileStatus) * codec_tiles(n);
 }
 
@@ -974,11 +974,18 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
     b.n = n;
     b.ntiles = (uint32_t)codec_tiles(n);
+    // segment length: long segments keep the look-back chain short and let phase 2 re-read from L2, but the
+    // launch should still fill the GPU about twice over (4 CTAs per SM resident)
+    const uint64_t want_ctas = (uint64_t)c->sm_count * 8;
+    uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
+    if (seg < 1) seg = 1;
+    if (seg > 16) seg = 16;                                                       // 128 KiB: 4 CTAs x 148 SMs x 128 KiB < L2
+    b.seg_tiles = (uint32_t)seg;
+    b.nsegs = (b.ntiles + b.seg_tiles - 1) / b.seg_tiles;
     // the look-back flags must start out invalid
-    MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.ntiles * sizeof(mbc::TileStatus), st));
-    const dim3 grid(b.ntiles, n_chunks, 1);
-    mbc::rle_single_pass<<<grid, mbc::kThreads, mbc::kStageBytes, st>>>(b);       // everything, for chunks that end up RLE
-    mbc::raw_fixup<<<grid, mbc::kThreads, 0, st>>>(b);                            // exits at once unless the chunk ended up Raw
+    MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.nsegs * sizeof(mbc::TileStatus), st));
+    mbc::rle_single_pass<<<dim3(b.nsegs, n_chunks, 1), mbc::kThreads, mbc::kStageBytes, st>>>(b);   // everything, for chunks that end up RLE
+    mbc::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc::kThreads, 0, st>>>(b);     // exits at once unless the chunk ended up Raw
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """Device DataChunk serializer throughput (f2): algorithmic bytes = n read + serialised bytes written."""
+import argparse
 import ctypes as C
 import json
 import os
@@ -11,6 +12,11 @@ import torch
 
 from distributedmandelbrot_b200 import _native as nat
 
+ap = argparse.ArgumentParser()
+ap.add_argument("--only", default=None, help="substring of the case name (for ncu captures)")
+ap.add_argument("--nb", type=int, nargs="*", default=[1, 64])
+ap.add_argument("--iters", type=int, default=10)
+args = ap.parse_args()
 nat.init(0)
 L = nat.lib()
 n = 4096 * 4096
@@ -30,15 +36,17 @@ nat.check(L.mb_render_u8(C.byref(t), 1, p.data_ptr(), 0, st))
 cases["chunk cfg4 (250,420) mrd=10000 [RLE, 3M runs]"] = p.clone()
 cases["noise [raw]"] = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
 cases["constant [RLE, 1 run]"] = torch.ones(n, dtype=torch.uint8, device="cuda")
-for nb in (1, 64):
+for nb in args.nb:
     ws_bytes = L.mb_serialize_workspace_bytes(n, nb)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     out = torch.empty(nb * stride, dtype=torch.uint8, device="cuda")
     info = torch.empty(nb * 32, dtype=torch.uint8, device="cuda")
     for name, one in cases.items():
+        if args.only and args.only not in name:
+            continue
         payload = one.repeat(nb)
         times = []
-        for _ in range(10):
+        for _ in range(args.iters):
             flush.fill_(1)                       # evict the payloads from the 126 MB L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
