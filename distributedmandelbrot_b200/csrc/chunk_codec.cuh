@@ -64,46 +64,58 @@ struct Batch {
     uint32_t nsegs;               // segments per chunk
 };
 
-// 4-bit mask of the bytes that differ between two words (SIMD byte compare, no per-byte loop)
-__device__ __forceinline__ uint32_t differ4(uint32_t a, uint32_t b)
+// 4-bit mask of the non-zero bytes of x (x = a ^ b: the bytes that differ), branch-free SWAR:
+// bit 7 of every non-zero byte, then the four bits gathered with one multiply
+__device__ __forceinline__ uint32_t nonzero4(uint32_t x)
 {
-    const uint32_t ne = __vcmpne4(a, b) & 0x01010101u;          // bit 0 of each byte = "differs"
-    return ((ne * 0x01020408u) >> 24) & 0xfu;                   // gather bits 0, 8, 16, 24 -> 0..3
+    const uint32_t h = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    return (((h >> 7) * 0x01020408u) >> 24) & 0xfu;
 }
 
-// 16-bit mask: bit j set iff byte j of the 16-byte span at `base` starts a run
-// (p[i] != p[i-1]; i = 0 always starts one).  `v` receives the 16 payload bytes (zero-padded),
-// `prev` the byte before the span.
-__device__ __forceinline__ uint32_t start_mask(const uint8_t *__restrict__ p, size_t base, size_t n, uint4 &v, uint32_t &prev)
+// 16-bit mask of the run starts inside 16 payload bytes v, `prev` being the byte before them
+__device__ __forceinline__ uint32_t starts16(const uint4 &v, uint32_t prev)
 {
-    v = make_uint4(0, 0, 0, 0);
-    prev = 0;
-    if (base >= n) return 0;
-    prev = base ? (uint32_t)p[base - 1] : 0u;
-    const bool full = base + kHalf <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0);
-    uint32_t mask;
-    if (full) {
-        v = *reinterpret_cast<const uint4 *>(p + base);
-        // the same 16 bytes shifted up by one byte, `prev` entering at the bottom
-        const uint32_t s0 = __byte_perm(prev, v.x, 0x6540), s1 = __byte_perm(v.x, v.y, 0x6543);
-        const uint32_t s2 = __byte_perm(v.y, v.z, 0x6543), s3 = __byte_perm(v.z, v.w, 0x6543);
-        mask = differ4(v.x, s0) | (differ4(v.y, s1) << 4) | (differ4(v.z, s2) << 8) | (differ4(v.w, s3) << 12);
-    } else {
-        uint8_t bytes[kHalf];
-        mask = 0;
-        uint8_t pb = (uint8_t)prev;
-#pragma unroll
-        for (int j = 0; j < kHalf; ++j) {
-            bytes[j] = (base + j < n) ? p[base + j] : 0;
-            if (base + j < n && bytes[j] != pb) mask |= 1u << j;
-            pb = bytes[j];
-        }
-        v.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
-        v.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | ((uint32_t)bytes[7] << 24);
-        v.z = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | ((uint32_t)bytes[11] << 24);
-        v.w = bytes[12] | (bytes[13] << 8) | (bytes[14] << 16) | ((uint32_t)bytes[15] << 24);
-    }
+    // the same 16 bytes shifted up by one byte, `prev` entering at the bottom
+    const uint32_t s0 = __byte_perm(prev, v.x, 0x6540), s1 = __byte_perm(v.x, v.y, 0x6543);
+    const uint32_t s2 = __byte_perm(v.y, v.z, 0x6543), s3 = __byte_perm(v.z, v.w, 0x6543);
+    return nonzero4(v.x ^ s0) | (nonzero4(v.y ^ s1) << 4) | (nonzero4(v.z ^ s2) << 8) | (nonzero4(v.w ^ s3) << 12);
+}
+
+// 32-bit mask: bit j set iff byte j of this thread's 32-byte span starts a run (p[i] != p[i-1];
+// i = 0 always starts one).  Fast path for spans that are whole and 16-byte aligned: two 128-bit
+// loads, the byte before the span comes from the neighbouring lane.  `prev` = byte before the span.
+__device__ __forceinline__ uint32_t span_mask_fast(const uint8_t *__restrict__ p, size_t base, uint4 &v0, uint4 &v1, uint32_t &prev)
+{
+    v0 = *reinterpret_cast<const uint4 *>(p + base);
+    v1 = *reinterpret_cast<const uint4 *>(p + base + kHalf);
+    prev = __shfl_up_sync(0xffffffffu, v1.w >> 24, 1);
+    if ((threadIdx.x & 31) == 0) prev = base ? (uint32_t)p[base - 1] : 0u;
+    uint32_t mask = starts16(v0, prev) | (starts16(v1, v0.w >> 24) << kHalf);
     if (base == 0) mask |= 1u;
+    return mask;
+}
+
+// the general path (ragged end of the payload, unaligned payload pointer): byte by byte, kept a real
+// loop so that the compiler branches around it instead of predicating it into the fast path
+__device__ __forceinline__ uint32_t span_mask_slow(const uint8_t *__restrict__ p, size_t base, size_t n, uint4 &v0, uint4 &v1, uint32_t &prev)
+{
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t mask = 0;
+    prev = 0;
+    if (base < n) {
+        prev = base ? (uint32_t)p[base - 1] : 0u;
+        uint32_t pb = prev;
+#pragma unroll 1
+        for (int j = 0; j < kBytesPerThread && base + j < n; ++j) {
+            const uint32_t c = p[base + j];
+            if (c != pb) mask |= 1u << j;
+            pb = c;
+            w[j >> 2] |= c << (8 * (j & 3));
+        }
+        if (base == 0) mask |= 1u;
+    }
+    v0 = make_uint4(w[0], w[1], w[2], w[3]);
+    v1 = make_uint4(w[4], w[5], w[6], w[7]);
     return mask;
 }
 
@@ -173,16 +185,23 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
     const uint32_t tile0 = seg * b.seg_tiles;
     const uint32_t ntl = b.ntiles - tile0 < b.seg_tiles ? b.ntiles - tile0 : b.seg_tiles;
 
+    // a tile is `regular` when all of it lies inside the payload and the payload is 16-byte aligned
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+
     // ---- phase 1: run starts of the whole segment --------------------------------------------------
     uint32_t seg_cnt = 0, seg_last = 0;
+    uint32_t busy = 0;                                   // bit k: my span of tile k holds a run start
     for (uint32_t k = 0; k < ntl; ++k) {
         uint4 v0, v1;
-        uint32_t pv0, pv1;
+        uint32_t pv;
         const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        uint32_t m = start_mask(p, base, n, v0, pv0);
-        m |= start_mask(p, base + kHalf, n, v1, pv1) << kHalf;
-        seg_cnt += __popc(m);
-        if (m) seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;           // positions grow with k
+        const bool regular = aligned && (size_t)(tile0 + k + 1) * kTile <= n;
+        const uint32_t m = regular ? span_mask_fast(p, base, v0, v1, pv) : span_mask_slow(p, base, n, v0, v1, pv);
+        if (m) {
+            seg_cnt += __popc(m);
+            seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;                // positions grow with k
+            busy |= 1u << k;
+        }
     }
     uint32_t seg_tot, seg_totlast;
     block_sum_max(seg_cnt, seg_last, w_cnt, w_last, seg_tot, seg_totlast);
@@ -239,22 +258,24 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
     }
     __syncthreads();
     const bool last_seg = (seg + 1 == b.nsegs);
-    const uint32_t runs_total = s_runs_before + seg_tot;           // the chunk's run count, on the last segment
+    uint32_t runs_before = s_runs_before, last_before = s_last_before;        // carried in registers, identical in every thread
+    const uint32_t runs_total = runs_before + seg_tot;                        // the chunk's run count, on the last segment
 
     // ---- phase 2: records of the runs that END in each tile of the segment -------------------------
     // run (g - 1) for every start with global index g >= 1, plus the chunk's last run on its last tile.
     // Record r lives at out[1 + 5r .. 1 + 5r + 5).  Tiles from which on RLE is already ruled out
-    // (5 * runs >= n keeps Raw, and runs only grow) are skipped.
+    // (5 * runs >= n keeps Raw, and runs only grow) are skipped, and so are tiles without a run start.
     for (uint32_t k = 0; k < ntl; ++k) {
-        const uint32_t runs_before = s_runs_before, last_before = s_last_before;
         if ((unsigned long long)runs_before * 5ull >= (unsigned long long)n) break;
         const uint32_t tile = tile0 + k;
         const bool is_last_tile = (tile + 1 == b.ntiles);
+        // also the barrier that releases the staging buffer and w_* of the previous tile
+        if (!__syncthreads_or((busy >> k) & 1u) && !is_last_tile) continue;
         uint4 v0, v1;
-        uint32_t prev, prev1;
+        uint32_t prev;
         const size_t base = (size_t)tile * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        uint32_t mask = start_mask(p, base, n, v0, prev);                       // L2 hits: phase 1 just read these lines
-        mask |= start_mask(p, base + kHalf, n, v1, prev1) << kHalf;
+        const bool regular = aligned && (size_t)(tile + 1) * kTile <= n;
+        uint32_t mask = regular ? span_mask_fast(p, base, v0, v1, prev) : span_mask_slow(p, base, n, v0, v1, prev);   // L2 hits
         const uint32_t cnt = __popc(mask);
         const uint32_t mylast = cnt ? (uint32_t)base + (31u - __clz(mask)) + 1u : 0u;
         // CTA-wide scan of (count, last start): inclusive in the warp, then across warps
@@ -264,7 +285,6 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
             const uint32_t c = __shfl_up_sync(0xffffffffu, inc, o), l = __shfl_up_sync(0xffffffffu, lastinc, o);
             if (lane >= (uint32_t)o) { inc += c; lastinc = lastinc > l ? lastinc : l; }
         }
-        __syncthreads();                                                         // previous tile: staging copied out, w_* consumed
         if (lane == 31) { w_cnt[warp] = inc; w_last[warp] = lastinc; }
         __syncthreads();
         uint32_t wbase = 0, wlast = 0, tot = 0, totlast = 0;
@@ -331,11 +351,8 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
                 reinterpret_cast<uint4 *>(dst + head)[q] = reinterpret_cast<const uint4 *>(src + head)[q];
             for (size_t q = head + body * 16 + threadIdx.x; q < nbytes; q += kThreads) dst[q] = src[q];
         }
-        if (threadIdx.x == 0) {                                                    // carry the prefix to the next tile
-            s_runs_before = runs_before + tot;
-            if (totlast) s_last_before = totlast;
-        }
-        __syncthreads();
+        runs_before += tot;                                                        // carry the prefix to the next tile
+        if (totlast) last_before = totlast;
     }
 
     // the last segment knows the run count: pick the codec, write header + length + classification
