@@ -30,7 +30,9 @@ constexpr int kHalf = 16;                              // one 128-bit load
 constexpr int kBytesPerThread = 2 * kHalf;             // two loads in flight per thread: 32 KiB per SM at 4 CTAs/SM
 constexpr int kTile = kThreads * kBytesPerThread;      // 8192 payload bytes per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kStageBytes = 5 * kTile + 32;            // worst case: every byte of the tile starts a run
+constexpr int kRound = 4096;                           // records assembled per round (a denser tile takes two rounds)
+constexpr int kStageRecBytes = 5 * kRound + 32;        // staging of one round's records (+ alignment slack)
+constexpr int kStageBytes = kStageRecBytes + 2 * (kTile + 8);   // ... followed by the tile's run-start offsets (uint16)
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -287,60 +289,64 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
         }
         if (lane == 31) { w_cnt[warp] = inc; w_last[warp] = lastinc; }
         __syncthreads();
-        uint32_t wbase = 0, wlast = 0, tot = 0, totlast = 0;
+        uint32_t wbase = 0, tot = 0, totlast = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t c = w_cnt[w], l = w_last[w];
-            if ((uint32_t)w < warp) { wbase += c; wlast = wlast > l ? wlast : l; }
+            if ((uint32_t)w < warp) wbase += c;
             tot += c;
             totlast = totlast > l ? totlast : l;
         }
         const uint32_t rank = wbase + inc - cnt;                       // starts of this tile before my span
-        uint32_t lastex = __shfl_up_sync(0xffffffffu, lastinc, 1);     // last start before my span, inside the tile
-        if (lane == 0) lastex = 0;
-        lastex = lastex > wlast ? lastex : wlast;
 
-        const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;           // first record this tile may write
-        uint32_t n_rec = tot - (runs_before ? 0u : (tot ? 1u : 0u));              // start 0 of the chunk closes nothing
-        if (is_last_tile) n_rec += 1u;
-        const size_t out_lo = 1 + (size_t)first_rec * 5;                          // byte range of this tile's records
-        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_lo) & 15u);   // stage congruent to out mod 16
+        // a) every thread appends the in-tile offsets of its run starts to a list (a short divergent loop:
+        //    runs cluster, a lane may hold ten starts while its neighbours hold none)
+        uint16_t *s_pos = reinterpret_cast<uint16_t *>(stage + kStageRecBytes);
         {
-            uint32_t prevstart = lastex ? lastex - 1u : (last_before ? last_before - 1u : 0u);
-            uint32_t g = runs_before + rank;                                      // global index of my first start
-            while (mask) {                                                        // one trip per run start, not per byte
+            uint32_t e = rank;
+            const uint32_t off = threadIdx.x * kBytesPerThread;
+            while (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const uint32_t pos = (uint32_t)base + j;
-                if (g >= 1) {
-                    const uint32_t len = pos - prevstart;                          // BitConverter.GetBytes(runLength): little-endian
-                    const uint32_t val = j ? byte_of(v0, v1, j - 1) : prev;        // runValue = the byte before the new start
-                    uint8_t *rec = stage + shift + (size_t)(g - 1 - first_rec) * 5;
-                    rec[0] = (uint8_t)len;
-                    rec[1] = (uint8_t)(len >> 8);
-                    rec[2] = (uint8_t)(len >> 16);
-                    rec[3] = (uint8_t)(len >> 24);
-                    rec[4] = (uint8_t)val;
-                }
-                prevstart = pos;
-                ++g;
+                s_pos[e++] = (uint16_t)(off + j);
             }
-            if (is_last_tile && threadIdx.x == 0) {
-                // the chunk's last run: from the last start anywhere to n
-                const uint32_t last_start = (totlast ? totlast : last_before) - 1u;
-                const uint32_t len = (uint32_t)n - last_start;
-                uint8_t *rec = stage + shift + (size_t)(runs_before + tot - 1 - first_rec) * 5;
+        }
+        __syncthreads();
+        // b) the list is turned into records by ALL threads, one list entry each (balanced, no divergence):
+        //    entry e is the start with global index g = runs_before + e and closes run g - 1, whose length
+        //    is this start minus the previous one and whose value is the byte before this start
+        const size_t tile_base = (size_t)tile * kTile;
+        const uint32_t skip = runs_before ? 0u : 1u;                               // start 0 of the chunk closes nothing
+        const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;           // first record this tile writes
+        const uint32_t n_rec = (tot > skip ? tot - skip : 0u) + (is_last_tile ? 1u : 0u);
+        for (uint32_t r0 = 0; r0 < n_rec; r0 += kRound) {
+            const uint32_t r1 = r0 + kRound < n_rec ? r0 + kRound : n_rec;        // records [r0, r1) of this tile in this round
+            const size_t out_lo = 1 + ((size_t)first_rec + r0) * 5;               // their byte range in the output
+            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_lo) & 15u);   // stage congruent to out mod 16
+            for (uint32_t r = r0 + threadIdx.x; r < r1; r += kThreads) {
+                uint32_t len, val;
+                const uint32_t e = r + skip;                                       // list entry that closes record r
+                if (e < tot) {
+                    const uint32_t pos = (uint32_t)tile_base + s_pos[e];
+                    const uint32_t before = e ? (uint32_t)tile_base + s_pos[e - 1] : last_before - 1u;
+                    len = pos - before;                                            // BitConverter.GetBytes(runLength): little-endian
+                    val = p[pos - 1];                                              // runValue (DataChunkSerializer.cs:84,98): an L1/L2 hit
+                } else {
+                    // the chunk's last run: from the last start anywhere to n
+                    const uint32_t last_start = (totlast ? totlast : last_before) - 1u;
+                    len = (uint32_t)n - last_start;
+                    val = p[n - 1];
+                }
+                uint8_t *rec = stage + shift + (size_t)(r - r0) * 5;
                 rec[0] = (uint8_t)len;
                 rec[1] = (uint8_t)(len >> 8);
                 rec[2] = (uint8_t)(len >> 16);
                 rec[3] = (uint8_t)(len >> 24);
-                rec[4] = p[n - 1];
+                rec[4] = (uint8_t)val;
             }
-        }
-        __syncthreads();
-        if (n_rec) {
+            __syncthreads();
             // copy out: bytes beyond n can never be part of an RLE result (5 * runs < n) and are dropped
-            size_t nbytes = (size_t)n_rec * 5;
+            size_t nbytes = (size_t)(r1 - r0) * 5;
             if (out_lo + nbytes > n + 1) nbytes = out_lo < n + 1 ? n + 1 - out_lo : 0;
             uint8_t *dst = out + out_lo;
             const uint8_t *src = stage + shift;
@@ -350,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
             for (size_t q = threadIdx.x; q < body; q += kThreads)
                 reinterpret_cast<uint4 *>(dst + head)[q] = reinterpret_cast<const uint4 *>(src + head)[q];
             for (size_t q = head + body * 16 + threadIdx.x; q < nbytes; q += kThreads) dst[q] = src[q];
+            if (r1 < n_rec) __syncthreads();                                       // the next round reuses the staging area
         }
         runs_before += tot;                                                        // carry the prefix to the next tile
         if (totlast) last_before = totlast;
