@@ -310,7 +310,7 @@ def main() -> None:
 
     sampler = ClockSampler(local)
     times = []
-    launches0, steals0 = fr.launches, fr.steals
+    launches0, steals0 = fr.launches, fr.steals_total
     if rank == 0:
         sampler.start()
     for _ in range(args.steps):
@@ -328,7 +328,7 @@ def main() -> None:
         times.append(allmax(e0.elapsed_time(e1)))            # max over ranks
     clocks = sampler.stop() if rank == 0 else None
     launches = torch.tensor([fr.launches - launches0], device=dev)
-    steals = torch.tensor([fr.steals - steals0], device=dev)
+    steals = torch.tensor([fr.steals_total - steals0], device=dev)
     if world > 1:
         dist.all_reduce(launches)
         dist.all_reduce(steals)

@@ -193,15 +193,33 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
     // ---- phase 1: run starts of the whole segment --------------------------------------------------
     uint32_t seg_cnt = 0, seg_last = 0;
     uint32_t busy = 0;                                   // bit k: my span of tile k holds a run start
-    for (uint32_t k = 0; k < ntl; ++k) {
+    // regular tiles first, unrolled so that several 128-bit loads per thread are in flight (this loop is
+    // the HBM stream of the kernel); a ragged last tile / unaligned payload takes the general path
+    uint32_t nreg = 0;
+    if (aligned) {
+        const size_t whole = n / kTile;                  // tiles that lie completely inside the payload
+        nreg = whole > tile0 ? (uint32_t)(whole - tile0 < ntl ? whole - tile0 : ntl) : 0u;
+    }
+#pragma unroll 4
+    for (uint32_t k = 0; k < nreg; ++k) {
         uint4 v0, v1;
         uint32_t pv;
         const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        const bool regular = aligned && (size_t)(tile0 + k + 1) * kTile <= n;
-        const uint32_t m = regular ? span_mask_fast(p, base, v0, v1, pv) : span_mask_slow(p, base, n, v0, v1, pv);
+        const uint32_t m = span_mask_fast(p, base, v0, v1, pv);
         if (m) {
             seg_cnt += __popc(m);
             seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;                // positions grow with k
+            busy |= 1u << k;
+        }
+    }
+    for (uint32_t k = nreg; k < ntl; ++k) {
+        uint4 v0, v1;
+        uint32_t pv;
+        const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
+        const uint32_t m = span_mask_slow(p, base, n, v0, v1, pv);
+        if (m) {
+            seg_cnt += __popc(m);
+            seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;
             busy |= 1u << k;
         }
     }

@@ -117,7 +117,8 @@ class FrameRenderer:
             self._launch = launch
         self.out = out if out is not None else torch.empty(spec.pixels, dtype=torch.int32, device=self.device)
         self.claimed: List[Tuple[int, int]] = []
-        self.steals = 0
+        self.steals = 0               # of the last render_stolen call
+        self.steals_total = 0         # accumulated over calls
         self.launches = 0
 
     # -- launching ---------------------------------------------------------------------------
@@ -151,6 +152,7 @@ class FrameRenderer:
                 buf, cap, C.byref(n_claims), C.byref(n_stolen)))
             self.claimed = coalesce([(buf[2 * k], buf[2 * k + 1]) for k in range(n_claims.value)])
             self.steals = n_stolen.value
+            self.steals_total += n_stolen.value
             self.launches += n_claims.value
             return
         while True:
@@ -161,6 +163,7 @@ class FrameRenderer:
                 break
             first, cnt, stolen = got
             self.steals += int(stolen)
+            self.steals_total += int(stolen)
             self._launch(first, cnt, self.out)
             self.launches += 1
             self.claimed.append((first, cnt))
