@@ -342,7 +342,10 @@ def main() -> None:
     # ---- device-resident frame with the exact periodicity shortcut (separately reported, never `value`) ----
     shortcut = None
     if not args.no_shortcut:
-        fs = FrameRenderer(spec.scaled(shortcut=True), device=local, rank=rank, world=world, bands_per_claim=4, depth=6, out=fr.out)
+        # the shortcut legs run on the persistent-warp kernel unless --refill 0 asks otherwise: lanes whose orbit closed a
+        # cycle are refilled at once instead of idling until the slowest lane of their patch is done (+12 % on cfg4)
+        sc_refill = True if args.refill is None else bool(args.refill)
+        fs = FrameRenderer(spec.scaled(shortcut=True, refill=sc_refill), device=local, rank=rank, world=world, bands_per_claim=4, depth=6, out=fr.out)
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
 
         def sc_step():
@@ -394,18 +397,19 @@ def main() -> None:
 
         def run_e2e(use_shortcut: bool):
             secs = []
+            use_refill = spec.refill if not use_shortcut else (True if args.refill is None else bool(args.refill))
             if world == 1:
-                worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None, shortcut=use_shortcut, refill=spec.refill)   # warm the pinned ring
+                worker.process_workloads(wl_all[:2], definition=spec.definition, consume=lambda *_: None, shortcut=use_shortcut, refill=use_refill)   # warm the pinned ring
                 for _ in range(args.e2e_steps):
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    worker.process_workloads(wl_all, definition=spec.definition, consume=consume, shortcut=use_shortcut, refill=spec.refill)
+                    worker.process_workloads(wl_all, definition=spec.definition, consume=consume, shortcut=use_shortcut, refill=use_refill)
                     torch.cuda.synchronize()
                     secs.append(time.perf_counter() - t0)
                 return secs, "worker.process_workloads (uint8 DataChunk payloads in pinned host memory, one per (level, mrd, ir, ii))"
             iw = InboxWorker(wl_all, definition=spec.definition, band_rows=spec.band_rows, rank=rank, world=world, device=local,
                              name=queue_name() + ("_s" if use_shortcut else "_e"), barrier=dist.barrier, shortcut=use_shortcut,
-                             bands_per_claim=4, depth=6, refill=spec.refill)
+                             bands_per_claim=4, depth=6, refill=use_refill)
             iw.rearm()
             iw.render()                                        # warm-up pass (staging buffers, page-locked mapping)
             for _ in range(args.e2e_steps):
@@ -491,6 +495,7 @@ def main() -> None:
             out["value_shortcut"] = {"value": useful / (shortcut["ms_per_step"] * 1e-3) / 1e9, "unit": METRIC,
                                      "ms_per_step": shortcut["ms_per_step"], "executed_updates": shortcut["executed_updates"],
                                      "executed_fraction": shortcut["executed_updates"] / useful,
+                                     "kernel": "escape_refill_kernel" if (args.refill is None or args.refill) else "escape_tiles_kernel",
                                      "note": "MB_TILE_PERIOD_SHORTCUT: bit-identical counts (parity suite runs with it on), credited work "
                                              "unchanged, executed work reduced; never used for `value` or `roofline`"}
         if e2e_sc is not None:
