@@ -86,7 +86,11 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
     int n = 0, lim = 0;
     OutT *dst = nullptr;
     bool alive = false;
+    bool pend = false;                 // PERIOD: orbit closed a cycle (result 0), store + refill still owed
     unsigned long long exec_acc = 0;
+    // PERIOD: a lane that closes a cycle has nothing to replay, so its store and refill can wait until
+    // kBatch lanes are free (or a lane needs the cold section anyway): one cold section serves them all
+    constexpr unsigned kBatch = 4;
 
     // Give every lane with `want` the next pixel of the stream; (nx, ny) receive z0 = c.  Pixels that
     // must not enter deferred blocks are evaluated and stored right here and the lane asks again.
@@ -156,7 +160,8 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
     // Resolve the lanes that raised an event after a trip s -> m -> e, store and refill; on return
     // (ex, ey, exx, eyy) hold every lane's state for the next trip and n is up to date.
     auto cold = [&](Real sxx_, Real sy_, Real mx_, Real my_, Real mA, Real mB, Real &ex, Real &ey, Real &exx, Real &eyy) {
-        bool fin = false;
+        bool fin = pend;                                             // parked since an earlier trip: result 0
+        pend = false;
         int result = 0;
         if (alive) {
             const bool tA = Defer<Real>::tripped(mA), tB = Defer<Real>::tripped(mB);
@@ -214,7 +219,7 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
             store_result<Real, OutT>(dst, result, lim);              // L2 merges the sector's other pixels
         }
         if (fin) {
-            if constexpr (PERIOD) exec_acc += (unsigned long long)(result ? result : n);
+            if constexpr (PERIOD) { if (alive) exec_acc += (unsigned long long)(result ? result : n); }   // parked lanes were counted when they parked
             alive = false;
         }
         Real nx = ex, ny = ey;
@@ -225,7 +230,24 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
         }
     };
 
-    while (__any_sync(kFull, alive)) {
+    // after a trip: does any lane need the cold section now?  (PERIOD: lanes on a cycle are parked first)
+    auto after_trip = [&](Real mA, Real mB, Real ex, Real ey) -> bool {
+        bool hard = alive && (Defer<Real>::tripped(mA) || Defer<Real>::tripped(mB) || (lim - n < 4 * K));
+        if constexpr (PERIOD) {
+            if (alive && !hard && O::same_bits(ex, sx) && O::same_bits(ey, sy)) {
+                alive = false;                                       // exact cycle: never escapes
+                pend = true;
+                exec_acc += (unsigned long long)(n + 2 * K);
+            }
+            const unsigned parked = __ballot_sync(kFull, pend);
+            const unsigned live = __ballot_sync(kFull, alive);
+            return __any_sync(kFull, hard) || __popc(parked) >= (int)kBatch || (parked && !live);
+        } else {
+            return __any_sync(kFull, hard);
+        }
+    };
+
+    while (__any_sync(kFull, alive || pend)) {
         // ---- trip 1: (x, y) -> a -> b
         Real ax = x, ay = y, axx = xx, ayy = yy;
 #pragma unroll
@@ -235,11 +257,7 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
 #pragma unroll
         for (int j = 0; j < K; ++j) update<Real>(bx, by, bxx, byy, cr, ci);
         Real mB = O::add(bxx, byy);
-        bool ev = alive && (Defer<Real>::tripped(mA) || Defer<Real>::tripped(mB) || (lim - n < 4 * K));
-        if constexpr (PERIOD) {
-            ev = ev || (alive && O::same_bits(bx, sx) && O::same_bits(by, sy));
-        }
-        if (__any_sync(kFull, ev)) {
+        if (after_trip(mA, mB, bx, by)) {
             cold(x, y, ax, ay, mA, mB, bx, by, bxx, byy);
             x = bx; y = by; xx = bxx; yy = byy;
             continue;
@@ -255,11 +273,7 @@ escape_refill_kernel(const __grid_constant__ TileArgs args, OutT *__restrict__ o
 #pragma unroll
         for (int j = 0; j < K; ++j) update<Real>(x, y, xx, yy, cr, ci);
         mB = O::add(xx, yy);
-        ev = alive && (Defer<Real>::tripped(mA) || Defer<Real>::tripped(mB) || (lim - n < 4 * K));
-        if constexpr (PERIOD) {
-            ev = ev || (alive && O::same_bits(x, sx) && O::same_bits(y, sy));
-        }
-        if (__any_sync(kFull, ev)) {
+        if (after_trip(mA, mB, x, y)) {
             cold(bx, by, ax, ay, mA, mB, x, y, xx, yy);
             continue;
         }
