@@ -974,9 +974,9 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
     b.n = n;
     b.ntiles = (uint32_t)codec_tiles(n);
-    // segment length: long segments keep the look-back chain short and let phase 2 re-read from L2, but the
-    // launch should still fill the GPU about twice over (4 CTAs per SM resident)
-    const uint64_t want_ctas = (uint64_t)c->sm_count * 8;
+    // segment length: long segments keep the look-back chain short (one dependent L2 round trip per 32
+    // predecessors) and let phase 2 re-read from L2; a single 16 MiB chunk still gets ~300 CTAs
+    const uint64_t want_ctas = (uint64_t)c->sm_count * 2;
     uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
     if (seg < 1) seg = 1;
     if (seg > 16) seg = 16;                                                       // 128 KiB: 4 CTAs x 148 SMs x 128 KiB < L2

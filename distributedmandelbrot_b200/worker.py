@@ -118,9 +118,11 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
             batch = list(itertools.islice(it, cap))
             if not batch:
                 return results
-            for (level, mrd, ir, ii) in batch:
-                _check_u32(level=level, mrd=mrd, index_real=ir, index_imag=ii, definition=definition)
-            rec = np.asarray(batch, dtype=np.uint32).reshape(-1, 4)
+            rec64 = np.asarray(batch, dtype=np.int64).reshape(-1, 4)          # one vectorised range check, not 4 per chunk
+            if (rec64 < 0).any() or (rec64 > 0xFFFFFFFF).any():
+                raise ValueError("workload fields must be uint32 (DistributerWorkload.cs:61-75)")
+            _check_u32(definition=definition)
+            rec = np.ascontiguousarray(rec64.astype(np.uint32))
             slab = _PAYLOADS.take(len(batch) * n)
             prev = nat.set_tile_flags(flags)
             try:
