@@ -975,11 +975,11 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.n = n;
     b.ntiles = (uint32_t)codec_tiles(n);
     // segment length: long segments keep the look-back chain short (one dependent L2 round trip per 32
-    // predecessors) and let phase 2 re-read from L2; a single 16 MiB chunk still gets ~300 CTAs
-    const uint64_t want_ctas = (uint64_t)c->sm_count * 2;
+    // predecessors) and let phase 2 re-read from L2; a single 16 MiB chunk still gets ~500 CTAs (one wave)
+    const uint64_t want_ctas = (uint64_t)c->sm_count * 4;
     uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
     if (seg < 1) seg = 1;
-    if (seg > 16) seg = 16;                                                       // 128 KiB: 4 CTAs x 148 SMs x 128 KiB < L2
+    if (seg > 8) seg = 8;                                                         // 64 KiB: 4 CTAs x 148 SMs x 64 KiB = 38 MB stays L2-resident beside the output stream (ncu: 16 tiles re-read 28-56 % from DRAM)
     b.seg_tiles = (uint32_t)seg;
     b.nsegs = (b.ntiles + b.seg_tiles - 1) / b.seg_tiles;
     // the look-back flags must start out invalid
