@@ -74,6 +74,7 @@ def process_workload(level: int, mrd: int, index_real: int, index_imag: int, *,
 _PAYLOADS = nat.PinnedPool()
 _SMALL_CHUNK = 1 << 20        # chunks up to 1 MiB go through the native list loop (mb_process_workloads_u8)
 _SLAB_BYTES = 64 << 20        # ... in page-locked slabs of at most this many payload bytes
+_LAUNCH_BYTES = 2 << 20       # ... about this much payload per launch: the last launch's copy is the exposed tail
 
 
 def process_workload_counts(level: int, mrd: int, index_real: int, index_imag: int, *,
@@ -127,7 +128,7 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
             prev = nat.set_tile_flags(flags)
             try:
                 nat.check(nat.lib().mb_process_workloads_u8(rec.ctypes.data_as(C.c_void_p), len(batch), int(definition),
-                                                            slab.ctypes.data_as(C.c_void_p), 0))
+                                                            slab.ctypes.data_as(C.c_void_p), _LAUNCH_BYTES))
             finally:
                 nat.set_tile_flags(prev)
             for j, w in enumerate(batch):
