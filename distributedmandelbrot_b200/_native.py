@@ -93,6 +93,7 @@ SIGNATURES = {
     "mb_hostframe_units": (_u32, [_vp]),
     "mb_hostframe_groups": (_u32, [_vp]),
     "mb_hostframe_reset": (_int, [_vp]),
+    "mb_hostframe_reset_active": (_int, [_vp, _u32]),
     "mb_hostframe_pin": (_int, [_vp]),
     "mb_hostframe_unpin": (_int, [_vp]),
     "mb_hostframe_mark_done": (_int, [_vp, _u32, _u32, C.POINTER(_u32), _u32, C.POINTER(_u32)]),
@@ -373,8 +374,12 @@ class HostFrame:
         check(lib().mb_hostframe_pin(self._h))
         self._pinned = True
 
-    def reset(self) -> None:
-        check(lib().mb_hostframe_reset(self._h))
+    def reset(self, active_units: int | None = None) -> None:
+        """Re-arm for another pass; with active_units only units [0, active_units) take part."""
+        if active_units is None:
+            check(lib().mb_hostframe_reset(self._h))
+        else:
+            check(lib().mb_hostframe_reset_active(self._h, int(active_units)))
 
     def mark_done(self, first: int, count: int = 1):
         """Publish units [first, first+count); returns the groups (chunks) this completed."""

@@ -86,15 +86,20 @@ void bind(mb_hostframe *f, void *base)
     f->total_bytes = f->h->total_bytes;
 }
 
-void arm(mb_hostframe *f)
+// units [0, active) take part in the next pass; the rest counts as delivered (a frame sized for B chunks
+// may carry fewer: the last batch of leases a Distributer hands out)
+void arm(mb_hostframe *f, uint32_t active)
 {
     const Header *h = f->h;
+    if (active > h->n_units) active = h->n_units;
     for (uint32_t g = 0; g < h->n_groups; ++g) {
         const uint32_t lo = g * h->units_per_group;
-        const uint32_t cnt = (h->n_units - lo < h->units_per_group) ? h->n_units - lo : h->units_per_group;
+        const uint32_t hi = lo + h->units_per_group < h->n_units ? lo + h->units_per_group : h->n_units;
+        const uint32_t cnt = active > lo ? (active < hi ? active - lo : hi - lo) : 0u;
         __atomic_store_n(&f->group_left[g], cnt, __ATOMIC_RELAXED);
     }
-    std::memset(f->unit_done, 0, h->n_units);
+    std::memset(f->unit_done, 0, active);
+    std::memset(f->unit_done + active, 1, h->n_units - active);
     __atomic_add_fetch(&f->h->epoch, 1u, __ATOMIC_RELEASE);
 }
 
@@ -139,7 +144,7 @@ int mb_hostframe_create(const char *name, uint64_t payload_bytes, uint32_t n_uni
     h->epoch = 0;
     bind(f, p);
     f->fd = fd;
-    arm(f);
+    arm(f, n_units);
     __atomic_store_n(&h->magic, kMagic, __ATOMIC_RELEASE);
     *out = f;
     return MB_OK;
@@ -183,7 +188,15 @@ uint32_t mb_hostframe_groups(mb_hostframe *f) { return f ? f->h->n_groups : 0; }
 int mb_hostframe_reset(mb_hostframe *f)
 {
     if (!f) return hfail(MB_ERR_INVALID, "NULL frame");
-    arm(f);
+    arm(f, f->h->n_units);
+    return MB_OK;
+}
+
+int mb_hostframe_reset_active(mb_hostframe *f, uint32_t active_units)
+{
+    if (!f) return hfail(MB_ERR_INVALID, "NULL frame");
+    if (active_units > f->h->n_units) return hfail(MB_ERR_INVALID, "%u active units, the frame has %u", active_units, f->h->n_units);
+    arm(f, active_units);
     return MB_OK;
 }
 

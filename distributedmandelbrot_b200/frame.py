@@ -305,8 +305,10 @@ class InboxWorker:
                  shortcut: bool = False, dtype: str = "f64", bands_per_claim: int = 4, depth: int = 6,
                  launch: Optional[Callable] = None, refill: bool = False):
         self.workloads = [tuple(int(v) for v in w) for w in workloads]
+        self.capacity = len(self.workloads)          # the shm frame is sized for this many chunks
         self.definition, self.band_rows = int(definition), int(band_rows)
         self.rank, self.world, self.dtype = rank, world, dtype
+        self._flags = (shortcut, refill)
         self.bands_per_claim, self.depth = bands_per_claim, depth
         self._barrier = barrier if barrier is not None else (lambda: None)
         self._launch = launch
@@ -334,8 +336,19 @@ class InboxWorker:
         self._barrier()
         if self.rank == 0:
             self.queue.reset(self.n_bands)
-            self.frame.reset()
+            self.frame.reset(self.n_bands)
         self._barrier()
+
+    def retarget(self, workloads) -> None:
+        """Point the same shm frame and queue at a NEW list of at most `capacity` workloads (collective;
+        every rank passes the same list) -- e.g. the next batch of leases from a Distributer."""
+        workloads = [tuple(int(v) for v in w) for w in workloads]
+        if not 0 < len(workloads) <= self.capacity:
+            raise ValueError(f"between 1 and {self.capacity} workloads per batch")
+        self.workloads = workloads
+        self.tiles, self.bands_per_chunk = workload_bands(workloads, self.definition, self.band_rows, *self._flags)
+        self.n_bands = len(self.tiles)
+        self.rearm()
 
     def payload(self, k: int):
         """uint8[definition^2] view of workload k's payload in the shared frame."""

@@ -21,6 +21,7 @@ missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import socket
 from struct import pack, unpack
 
@@ -131,11 +132,11 @@ def process_workloads(workloads, *, definition: int = DEFINITION, consume=None, 
                                                             slab.ctypes.data_as(C.c_void_p), _LAUNCH_BYTES))
             finally:
                 nat.set_tile_flags(prev)
-            for j, w in enumerate(batch):
-                payload = slab[j * n:(j + 1) * n]
-                if consume is None:
-                    results.append(payload.copy())
-                else:
+            rows = slab.reshape(len(batch), n)                               # one view per payload, made in C
+            if consume is None:
+                results.extend(row.copy() for row in rows)
+            else:
+                for w, payload in zip(batch, rows):
                     consume(w, payload)
     import torch
     device = torch.device("cuda", dev_index)
@@ -340,6 +341,83 @@ def run_pipelined(addr: str, port: int, *, depth: int = 4, verbose: bool = True)
     return count
 
 
+def run_inbox(addr: str, port: int, *, rank: int, world: int, device: int | None = None, barrier=None, share=None,
+              batch: int | None = None, definition: int = DEFINITION, verbose: bool = True, launch=None,
+              shortcut: bool = False, name: str | None = None) -> int:
+    """ONE worker made of all GPUs of a box (SURVEY.md 8e + f4), behind an unmodified Distributer.
+
+    Rank 0 leases a batch of workloads over the reference protocol (one short connection per lease,
+    Distributer.cs:358-392) and shares the list; the chunks of the batch are cut into row bands and
+    rendered by ALL ranks through the shared work-stealing queue into one page-locked shm frame
+    (frame.InboxWorker), so an expensive chunk is finished by eight GPUs instead of occupying one; the
+    rank that delivers a chunk's last band sends its 16 MiB payload back (its own connection,
+    Distributer.cs:397-458).  With N independent reference workers a level's tail is one GPU grinding
+    through the last deep chunk; here the tail is that chunk divided by N.
+
+    barrier() / share(obj) are the two collectives needed (torch.distributed.barrier and an object
+    broadcast from rank 0); `launch` is the CPU test hook of InboxWorker.  Returns the number of
+    payloads this rank sent."""
+    from .frame import InboxWorker
+    say = print if verbose and rank == 0 else (lambda *a, **k: None)
+    barrier = barrier if barrier is not None else (lambda: None)
+    share = share if share is not None else (lambda obj: obj)
+    batch = batch if batch is not None else max(2, 2 * world)
+    sent = 0
+
+    def lease_batch():
+        got = []
+        while len(got) < batch:
+            w = request_workload(addr, port)
+            if w is None:
+                break
+            got.append(w)
+        return got
+
+    def send_back(w, payload):
+        nonlocal sent
+        ok = return_workload(addr, port, w, payload)
+        sent += 1
+        if verbose:
+            print("Sent response" if ok else "Response rejected", w, flush=True)
+
+    iw = None
+    while True:
+        leases = share(lease_batch() if rank == 0 else None)
+        if not leases:
+            say("No workload was available, ending program")
+            break
+        say("Workloads received:", leases)
+        if iw is None:
+            # placeholders up to `batch`: the shm frame is sized once, later batches only retarget it
+            first = list(leases) + [leases[-1]] * (batch - len(leases))
+            iw = InboxWorker(first, definition=definition, rank=rank, world=world, device=device, barrier=barrier,
+                             shortcut=shortcut, launch=launch, name=name)
+        iw.retarget(leases)
+        iw.render(consume=send_back)
+        barrier()
+        if rank == 0 and iw.missing():                 # bands a rank claimed and never delivered
+            iw.repair(consume=send_back)
+        barrier()
+    if iw is not None:
+        iw.close()
+    return sent
+
+
+def _inbox_main(addr: str, port: int, pipeline_unused: int = 0) -> None:
+    """Entry point of one rank of `worker --gpus N --inbox` (environment set by the launcher)."""
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)          # control plane only: two tiny collectives per batch
+
+    def share(obj):
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    run_inbox(addr, port, rank=rank, world=world, device=rank, barrier=dist.barrier, share=share)
+    dist.destroy_process_group()
+
+
 def main(argv=None) -> None:
     """(.py:178-184) prompts `Server Addr> ` / `Server Port> ` like the reference; --addr/--port/
     --device skip the prompts."""
@@ -351,10 +429,28 @@ def main(argv=None) -> None:
     ap.add_argument("--pipeline", type=int, default=0, metavar="DEPTH",
                     help="keep DEPTH leases in flight (0 = one at a time, like the reference)")
     ap.add_argument("--gpus", type=int, default=0, metavar="N",
-                    help="start one worker process per GPU for devices 0..N-1 (today: N copies of the reference worker)")
+                    help="start one worker process per GPU for devices 0..N-1 (N independent workers, like N reference workers)")
+    ap.add_argument("--inbox", action="store_true",
+                    help="with --gpus N: the N GPUs act as ONE worker -- leases are rendered band by band by all of them "
+                         "(frame.InboxWorker) instead of one chunk per GPU")
+    ap.add_argument("--inbox-rank", type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args(argv)
     addr = args.addr if args.addr is not None else input("Server Addr> ")
     port = args.port if args.port is not None else int(input("Server Port> "))
+    if args.inbox_rank is not None:
+        _inbox_main(addr, port)
+        return
+    if args.gpus > 0 and args.inbox:
+        import subprocess
+        import sys
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29400 + os.getpid() % 2000), WORLD_SIZE=str(args.gpus))
+        procs = [subprocess.Popen([sys.executable, "-m", "distributedmandelbrot_b200.worker", "--addr", addr, "--port", str(port),
+                                   "--inbox-rank", str(k)], env=dict(env, RANK=str(k), LOCAL_RANK=str(k)))
+                 for k in range(args.gpus)]
+        codes = [p.wait() for p in procs]
+        if any(codes):
+            raise SystemExit(f"worker exit codes: {codes}")
+        return
     if args.gpus > 0:
         # one process per GPU, exactly like running N reference workers against the same Distributer
         import subprocess

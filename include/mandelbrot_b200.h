@@ -328,6 +328,9 @@ uint64_t mb_hostframe_bytes(mb_hostframe *f);
 uint32_t mb_hostframe_units(mb_hostframe *f);
 uint32_t mb_hostframe_groups(mb_hostframe *f);
 int mb_hostframe_reset(mb_hostframe *f);                                  /* re-arm for another pass (one rank, between barriers) */
+/* re-arm with only units [0, active_units) taking part (the rest counts as delivered): a frame sized for
+ * B chunks may carry a shorter last batch */
+int mb_hostframe_reset_active(mb_hostframe *f, uint32_t active_units);
 /* page-lock / unlock THIS process's mapping on the bound device (cudaHostRegister) */
 int mb_hostframe_pin(mb_hostframe *f);
 int mb_hostframe_unpin(mb_hostframe *f);

@@ -123,3 +123,87 @@ def test_constants_match_reference():
     assert (worker.WORKLOAD_ACCEPT_CODE, worker.WORKLOAD_REJECT_CODE) == (0x20, 0x21)
     assert worker.DATA_CHUNK_SIZE == 16_777_216
     assert struct.calcsize("<IIII") == 16
+
+
+# ---- all GPUs of a box as ONE worker behind the Distributer (worker.run_inbox) ---------------------
+
+def _inbox_rank(rank, world, port, dport, name, wl):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle
+    import torch.distributed as dist
+    from distributedmandelbrot_b200 import worker
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    state = {}
+
+    def share(obj):
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        state["leases"] = box[0]
+        return box[0]
+
+    cache = {}
+
+    def stub(first, count, frame):
+        # stands in for the CUDA dispatch loop: bands of the current leases, from the CPU oracle
+        d, rows = 4096, 256
+        bpc = d // rows
+        for u in range(first, first + count):
+            w = state["leases"][u // bpc]
+            if w not in cache:
+                cache[w] = oracle.process_workload(*w, d)
+            lo = (u % bpc) * rows * d
+            frame[u * rows * d:(u + 1) * rows * d] = cache[w][lo:lo + rows * d]
+
+    sent = worker.run_inbox("127.0.0.1", dport, rank=rank, world=world, barrier=dist.barrier, share=share,
+                            launch=stub, verbose=False, name=name, batch=4)
+    counts = [None] * world
+    dist.all_gather_object(counts, sent)
+    assert sum(counts) == len(wl)
+    dist.destroy_process_group()
+
+
+def test_inbox_worker_behind_the_distributer(oracle, tmp_path):
+    """Two ranks act as ONE worker: rank 0 leases batches of 4 (then a short last batch of 1), the bands of
+    every chunk are delivered by both ranks into the shared frame, and whichever rank completes a chunk
+    returns its 16 MiB payload over the reference protocol."""
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    wl = [(4, 8, 0, 0), (4, 8, 3, 0), (4, 6, 0, 3), (4, 7, 3, 3), (8, 5, 0, 0)]
+    fd = FakeDistributer(wl)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    try:
+        mp.spawn(_inbox_rank, args=(2, port, fd.port, f"/mbw_test_{os.getpid()}", wl), nprocs=2, join=True)
+    finally:
+        fd.close()
+    assert fd.error is None, fd.error
+    assert sorted(fd.completed) == sorted(wl) and not fd.leases
+    for w in wl:
+        data = np.frombuffer(fd.completed[w], dtype=np.uint8)
+        assert np.array_equal(data, oracle.process_workload(*w, 4096)), w
+    assert [e for e in fd.log if e[0] == "lease"] == [("lease", w) for w in wl]
+
+
+@pytest.mark.gpu
+def test_inbox_worker_on_gpu_behind_the_distributer(gpu, oracle):
+    """run_inbox on the real CUDA path (one rank): batches of leases rendered band by band into the shared
+    page-locked frame, payloads returned over the protocol, a shorter last batch retargets the same frame."""
+    import os
+    from distributedmandelbrot_b200 import worker
+    wl = WORKLOADS + [(4, 64, 1, 2), (4, 9, 3, 3)]
+    fd = FakeDistributer(wl)
+    try:
+        sent = worker.run_inbox("127.0.0.1", fd.port, rank=0, world=1, device=0, verbose=False, batch=3,
+                                name=f"/mbw_gpu_{os.getpid()}")
+    finally:
+        fd.close()
+    assert fd.error is None, fd.error
+    assert sent == len(wl) and sorted(fd.completed) == sorted(wl)
+    for w in wl:
+        assert np.array_equal(np.frombuffer(fd.completed[w], dtype=np.uint8), oracle.process_workload(*w, 4096)), w
