@@ -27,6 +27,7 @@ thread_local int g_device = -1;
 thread_local uint32_t g_tile_flags = 0;     // mb_set_period_shortcut: flags of the one-call entry points' tiles
 thread_local unsigned long long *g_executed = nullptr;   // mb_set_executed_counter (shortcut launches only)
 thread_local double g_first_claim = 0.0, g_last_claim = 0.0;   // mb_frame_last_stats
+thread_local const mb_tile *g_tiles_dev_hint = nullptr;        // launch_tiles: descriptors already on the device (mb_process_workloads_u8)
 
 double now_monotonic()
 {
@@ -67,6 +68,8 @@ struct DeviceCtx {
     size_t scratch_bytes = 0;
     unsigned long long *counters = nullptr;   // patch counters of the lane-refill kernel, one per launch in flight
     uint32_t next_counter = 0;
+    mb_tile *desc = nullptr;            // descriptors of one mb_process_workloads_u8 call, uploaded once
+    size_t desc_tiles = 0;
     void *stage[16] = {};               // per-slot device staging of mb_frame_render_u8_host
     size_t stage_bytes[16] = {};
     std::mutex mu;
@@ -162,9 +165,14 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
     std::memset(&args, 0, sizeof(args));
     args.executed = g_executed;          // only read by the shortcut instantiations
     mb_tile *tiles_dev = nullptr;
+    const mb_tile *hint = g_tiles_dev_hint;          // the caller uploaded these descriptors itself (one copy for many launches)
+    g_tiles_dev_hint = nullptr;
+    const bool owned = (hint == nullptr);
     if (n_tiles <= (uint32_t)mbk::kInlineTiles) {
         args.n_inline = n_tiles;
         std::memcpy(args.inl, tiles, sizeof(mb_tile) * n_tiles);
+    } else if (hint) {
+        tiles_dev = const_cast<mb_tile *>(hint);
     } else {
         const size_t bytes = sizeof(mb_tile) * (size_t)n_tiles;
         MB_CUDA(cudaMallocAsync((void **)&tiles_dev, bytes, st));
@@ -196,7 +204,7 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
         MB_V(1, 16, 2, 2, 12) MB_V(2, 64, 2, 2, 12) MB_V(3, 32, 1, 2, 24) MB_V(4, 32, 2, 4, 6) MB_V(5, 32, 4, 1, 12)
         MB_V(6, 32, 1, 1, 32) MB_V(7, 32, 2, 2, 8) MB_V(8, 0, 2, 2, 12) MB_V(9, 32, 4, 2, 6)
 #undef MB_V
-        if (tiles_dev) MB_CUDA(cudaFreeAsync(tiles_dev, st));
+        if (tiles_dev && owned) MB_CUDA(cudaFreeAsync(tiles_dev, st));
         return rc;
     }
 #endif
@@ -234,7 +242,7 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
             e = cudaGetLastError();
             if (e != cudaSuccess) rc = fail(MB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         }
-        if (tiles_dev) cudaFreeAsync(tiles_dev, st);
+        if (tiles_dev && owned) cudaFreeAsync(tiles_dev, st);
         return rc;
     }
     const uint64_t ctas64 = (uint64_t)((mw + kCtaW - 1) / kCtaW) * ((mh + kCtaH - 1) / kCtaH);
@@ -259,7 +267,7 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
         }
         if (err != cudaSuccess) rc = fail(MB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     }
-    if (tiles_dev) cudaFreeAsync(tiles_dev, st);      // also on the error paths: never leak the descriptor batch
+    if (tiles_dev && owned) cudaFreeAsync(tiles_dev, st);      // also on the error paths: never leak the descriptor batch
     return rc;
 }
 
@@ -340,6 +348,9 @@ void mb_shutdown(void)
         if (c.scratch) cudaFree(c.scratch);
         if (c.counters) cudaFree(c.counters);
         c.counters = nullptr;
+        if (c.desc) cudaFree(c.desc);
+        c.desc = nullptr;
+        c.desc_tiles = 0;
         for (int k = 0; k < 16; ++k) { if (c.stage[k]) cudaFree(c.stage[k]); c.stage[k] = nullptr; c.stage_bytes[k] = 0; }
         if (c.stream) cudaStreamDestroy(c.stream);
         for (auto &ln : c.lanes) { if (ln) cudaStreamDestroy(ln); ln = nullptr; }
@@ -604,31 +615,41 @@ int mb_process_workloads_u8(const uint32_t *workloads, uint32_t n_workloads, uin
         c->stage_bytes[k] = n * group;
     }
     EventSet evs;
-    if (evs.add(kSlots)) return fail(MB_ERR_CUDA, "cudaEventCreate failed");
-    std::vector<mb_tile> tiles(group);
+    if (evs.add(kSlots + 1)) return fail(MB_ERR_CUDA, "cudaEventCreate failed");
+    // geometry of every workload on the host (C, strict binary64), ONE descriptor upload for the whole call
+    std::vector<mb_tile> tiles(n_workloads);
+    for (uint32_t k = 0; k < n_workloads; ++k) {
+        const uint32_t *w = workloads + 4 * (size_t)k;                        // level, mrd, indexReal, indexImag (DistributerWorkload.cs:9-29)
+        if (w[1] == 0) return fail(MB_ERR_INVALID, "workload %u: mrd == 0 divides by zero in the uint8 scaling (.py:96)", k);
+        if ((rc = mb_chunk_geometry(w[0], w[2], w[3], definition, w[1], &tiles[k]))) return rc;
+        tiles[k].out_offset = (uint64_t)(k % group) * n;                      // inside its launch's staging buffer
+        tiles[k].flags = g_tile_flags;
+    }
+    if (c->desc_tiles < n_workloads) {
+        if (c->desc) { MB_CUDA(cudaFree(c->desc)); c->desc = nullptr; c->desc_tiles = 0; }
+        MB_CUDA(cudaMalloc((void **)&c->desc, sizeof(mb_tile) * (size_t)n_workloads));
+        c->desc_tiles = n_workloads;
+    }
+    MB_CUDA(cudaMemcpyAsync(c->desc, tiles.data(), sizeof(mb_tile) * (size_t)n_workloads, cudaMemcpyHostToDevice, c->stream));
+    MB_CUDA(cudaEventRecord(evs.ev[kSlots], c->stream));
+    for (uint32_t k = 0; k < kLanes; ++k) MB_CUDA(cudaStreamWaitEvent(c->lanes[k], evs.ev[kSlots], 0));
     uint32_t launches = 0;
     int result = MB_OK;
     for (uint32_t first = 0; first < n_workloads && result == MB_OK; first += group, ++launches) {
         const uint32_t cnt = n_workloads - first < group ? n_workloads - first : group;
-        for (uint32_t j = 0; j < cnt && result == MB_OK; ++j) {
-            const uint32_t *w = workloads + 4 * (size_t)(first + j);          // level, mrd, indexReal, indexImag (DistributerWorkload.cs:9-29)
-            if (w[1] == 0) { result = fail(MB_ERR_INVALID, "workload %u: mrd == 0 divides by zero in the uint8 scaling (.py:96)", first + j); break; }
-            result = mb_chunk_geometry(w[0], w[2], w[3], definition, w[1], &tiles[j]);
-            tiles[j].out_offset = (uint64_t)j * n;
-            tiles[j].flags = g_tile_flags;
-        }
-        if (result) break;
         const uint32_t slot = launches % kSlots;
         if (launches >= kSlots) {                                             // the slot's previous copy must have left the buffer
             cudaError_t e = cudaEventSynchronize(evs.ev[slot]);
             if (e != cudaSuccess) { result = fail(MB_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e)); break; }
         }
         cudaStream_t lane = c->lanes[launches % kLanes];
-        if ((result = mb_render_u8(tiles.data(), cnt, static_cast<uint8_t *>(c->stage[slot]), MB_DTYPE_F64, lane))) break;
+        g_tiles_dev_hint = c->desc + first;
+        if ((result = mb_render_u8(tiles.data() + first, cnt, static_cast<uint8_t *>(c->stage[slot]), MB_DTYPE_F64, lane))) break;
         cudaError_t e = cudaMemcpyAsync(host_out + (size_t)first * n, c->stage[slot], (size_t)cnt * n, cudaMemcpyDeviceToHost, lane);
         if (e == cudaSuccess) e = cudaEventRecord(evs.ev[slot], lane);
         if (e != cudaSuccess) result = fail(MB_ERR_CUDA, "payload copy: %s", cudaGetErrorString(e));
     }
+    g_tiles_dev_hint = nullptr;
     for (uint32_t k = 0; k < kLanes; ++k) {
         cudaError_t e = cudaStreamSynchronize(c->lanes[k]);
         if (e != cudaSuccess && !result) result = fail(MB_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
