@@ -607,7 +607,7 @@ int mb_process_workloads_u8(const uint32_t *workloads, uint32_t n_workloads, uin
     uint32_t group = (uint32_t)(launch_bytes / n);
     if (group == 0) group = 1;
     if (group > 1024) group = 1024;
-    constexpr uint32_t kSlots = 4, kLanes = 4;
+    constexpr uint32_t kSlots = 8, kLanes = 4;     // 8 staging buffers: a frame of 8 launches is enqueued without a host-side wait
     for (uint32_t k = 0; k < kSlots; ++k) {
         if (c->stage_bytes[k] >= n * group) continue;
         if (c->stage[k]) { MB_CUDA(cudaFree(c->stage[k])); c->stage[k] = nullptr; c->stage_bytes[k] = 0; }
