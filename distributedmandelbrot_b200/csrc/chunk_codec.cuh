@@ -32,10 +32,7 @@ constexpr int kTile = kThreads * kBytesPerThread;      // 8192 payload bytes per
 constexpr int kWarps = kThreads / 32;
 constexpr int kRound = 4096;                           // records assembled per round (a denser tile takes two rounds)
 constexpr int kStageRecBytes = 5 * kRound + 32;        // staging of one round's records (+ alignment slack)
-constexpr int kMaxSegTiles = 16;                       // tiles per segment (128 KiB per CTA)
-constexpr int kListBytes = 2 * (kTile + 8);            // the tile's run-start offsets (uint16)
-constexpr int kMaskBytes = 4 * kMaxSegTiles * kThreads;   // every thread's start masks of the segment's tiles, phase 1 -> phase 2
-constexpr int kStageBytes = kStageRecBytes + kListBytes + kMaskBytes;
+constexpr int kStageBytes = kStageRecBytes + 2 * (kTile + 8);   // ... followed by the tile's run-start offsets (uint16)
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -172,9 +169,8 @@ __device__ __forceinline__ void block_sum_max(uint32_t c, uint32_t l, uint32_t *
 //   phase 1  streams the segment once from HBM and counts its run starts (+ position of the last one);
 //   look-back  one decoupled look-back per SEGMENT (a few hundred per chunk, not thousands of tiles:
 //            the chain is short and several chunks are in flight at once);
-//   phase 2  walks the segment's tiles again -- their run-start masks were kept in shared memory, the
-//            payload itself is not read a second time (only the one value byte per run, an L1/L2 hit) --
-//            and emits the records, carrying the running (runs, last start) from tile to tile.
+//   phase 2  walks the segment's tiles again -- now L2 hits, the segment was just read -- and emits the
+//            records, carrying the running (runs, last start) in shared memory from tile to tile.
 // Segment ids follow blockIdx.x: blocks are dispatched in increasing linear index, so every
 // predecessor a segment waits for is running or done (the usual decoupled-look-back assumption).
 __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
@@ -193,7 +189,6 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
 
     // a tile is `regular` when all of it lies inside the payload and the payload is 16-byte aligned
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(stage + kStageRecBytes + kListBytes);   // [tile of the segment][thread]
 
     // ---- phase 1: run starts of the whole segment --------------------------------------------------
     uint32_t seg_cnt = 0, seg_last = 0;
@@ -211,7 +206,6 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
         uint32_t pv;
         const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
         const uint32_t m = span_mask_fast(p, base, v0, v1, pv);
-        s_mask[k * kThreads + threadIdx.x] = m;          // phase 2 reuses it: the payload is read from HBM once, and only once
         if (m) {
             seg_cnt += __popc(m);
             seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;                // positions grow with k
@@ -223,7 +217,6 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
         uint32_t pv;
         const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
         const uint32_t m = span_mask_slow(p, base, n, v0, v1, pv);
-        s_mask[k * kThreads + threadIdx.x] = m;
         if (m) {
             seg_cnt += __popc(m);
             seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;
@@ -298,8 +291,11 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
         const bool is_last_tile = (tile + 1 == b.ntiles);
         // also the barrier that releases the staging buffer and w_* of the previous tile
         if (!__syncthreads_or((busy >> k) & 1u) && !is_last_tile) continue;
+        uint4 v0, v1;
+        uint32_t prev;
         const size_t base = (size_t)tile * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        uint32_t mask = s_mask[k * kThreads + threadIdx.x];                       // from phase 1 (same thread: no barrier needed)
+        const bool regular = aligned && (size_t)(tile + 1) * kTile <= n;
+        uint32_t mask = regular ? span_mask_fast(p, base, v0, v1, prev) : span_mask_slow(p, base, n, v0, v1, prev);   // L2 hits
         const uint32_t cnt = __popc(mask);
         const uint32_t mylast = cnt ? (uint32_t)base + (31u - __clz(mask)) + 1u : 0u;
         // CTA-wide scan of (count, last start): inclusive in the warp, then across warps

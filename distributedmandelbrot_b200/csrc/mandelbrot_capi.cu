@@ -1000,16 +1000,11 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     const uint64_t want_ctas = (uint64_t)c->sm_count * 4;
     uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
     if (seg < 1) seg = 1;
-    if (seg > mbc::kMaxSegTiles) seg = mbc::kMaxSegTiles;                         // 128 KiB per CTA; 8 was tried: run-dense chunks +1.5 %, constant chunks -16 % (longer look-back chain)
+    if (seg > 16) seg = 16;                                                       // 128 KiB per CTA; 8 was tried: run-dense chunks +1.5 %, constant chunks -16 % (longer look-back chain)
     b.seg_tiles = (uint32_t)seg;
     b.nsegs = (b.ntiles + b.seg_tiles - 1) / b.seg_tiles;
     // the look-back flags must start out invalid
     MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.nsegs * sizeof(mbc::TileStatus), st));
-    static bool smem_opt_in = false;                                              // 52 KiB of dynamic shared memory: above the 48 KiB default
-    if (!smem_opt_in) {
-        MB_CUDA(cudaFuncSetAttribute(mbc::rle_single_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, mbc::kStageBytes));
-        smem_opt_in = true;
-    }
     mbc::rle_single_pass<<<dim3(b.nsegs, n_chunks, 1), mbc::kThreads, mbc::kStageBytes, st>>>(b);   // everything, for chunks that end up RLE
     mbc::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc::kThreads, 0, st>>>(b);     // exits at once unless the chunk ended up Raw
     MB_CUDA(cudaGetLastError());
