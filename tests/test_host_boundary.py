@@ -187,3 +187,22 @@ def test_pinned_pool_recycles_blocks(native):
     del hoard
     gc.collect()
     assert small.outstanding == 0
+
+
+def test_bench_parity_guard_is_oracle_derived():
+    """bench.py's frame-sum guard reads the CPU oracle's per-chunk digests; neither bench.py nor the GPU
+    tests hold a frame-level constant recorded from a CUDA build."""
+    import importlib.util
+    import json
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in ("cfg2", "cfg3", "cfg4", "cfg5"):
+        doc = json.load(open(os.path.join(root, "tests", "golden", f"fullsize_{name}.json")))
+        assert doc["complete"] and bench.expected_useful(name) == doc["useful_total"] == sum(c["useful"] for c in doc["chunks"].values())
+    assert bench.expected_useful("cfg4_4x4") is None
+    for path in ("bench.py", os.path.join("tests", "test_gpu_parity.py"), os.path.join("tests", "test_gpu_fullsize.py")):
+        text = open(os.path.join(root, path)).read()
+        assert not re.search(r"\b\d{1,3}(_\d{3}){3,}\b", text), f"{path} holds a large literal constant"
