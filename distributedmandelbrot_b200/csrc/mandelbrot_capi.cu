@@ -11,6 +11,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <type_traits>
@@ -231,6 +232,20 @@ int launch_tiles(const mb_tile *tiles, uint32_t n_tiles, OutT *out_dev, int dtyp
             const unsigned long long cap = (unsigned long long)c->sm_count * kRefillCtas;
             if (ctas > cap) ctas = cap;
             const bool period = (tiles[0].flags & MB_TILE_PERIOD_SHORTCUT) != 0;
+#ifdef MB_TUNING_VARIANTS
+            // development-only: MB_REFILL_CTAS=10 selects the 51-register build of the refill kernel
+            static const int tune_ctas = getenv("MB_REFILL_CTAS") ? atoi(getenv("MB_REFILL_CTAS")) : 0;
+            if (tune_ctas == 10 && dtype == MB_DTYPE_F64) {
+                unsigned long long ctas10 = (slots + 3) / 4;
+                if (ctas10 > (unsigned long long)c->sm_count * 10) ctas10 = (unsigned long long)c->sm_count * 10;
+                if (period) mbk::escape_refill_kernel<double, OutT, 10, true><<<dim3((unsigned)ctas10), 128, 0, st>>>(args, out_dev);
+                else mbk::escape_refill_kernel<double, OutT, 10, false><<<dim3((unsigned)ctas10), 128, 0, st>>>(args, out_dev);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) rc = fail(MB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+                if (tiles_dev && owned) cudaFreeAsync(tiles_dev, st);
+                return rc;
+            }
+#endif
             const dim3 grid((unsigned)ctas, 1, 1), block(128, 1, 1);
             if (dtype == MB_DTYPE_F64) {
                 if (period) mbk::escape_refill_kernel<double, OutT, kRefillCtas, true><<<grid, block, 0, st>>>(args, out_dev);
