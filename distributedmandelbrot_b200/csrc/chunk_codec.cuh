@@ -121,18 +121,6 @@ __device__ __forceinline__ uint32_t span_mask_slow(const uint8_t *__restrict__ p
     return mask;
 }
 
-__device__ __forceinline__ uint32_t byte_of(const uint4 &v, int j)
-{
-    const uint32_t w = j < 8 ? (j < 4 ? v.x : v.y) : (j < 12 ? v.z : v.w);
-    return (w >> (8 * (j & 3))) & 0xffu;
-}
-
-// byte j (0..31) of a thread's 32-byte span held in two 128-bit registers
-__device__ __forceinline__ uint32_t byte_of(const uint4 &v0, const uint4 &v1, int j)
-{
-    return j < kHalf ? byte_of(v0, j) : byte_of(v1, j - kHalf);
-}
-
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
 {
     return *reinterpret_cast<const volatile unsigned long long *>(p);
