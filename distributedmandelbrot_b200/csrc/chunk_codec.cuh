@@ -7,32 +7,48 @@
 //     byte 0 = codec: 0x00 raw -> the n payload bytes ; 0x01 RLE -> (uint32 LE runLength, uint8
 //     value) records, one per maximal run.  Raw wins ties (`<` with Raw first, DataChunk.cs:188).
 //
-// ONE pass over HBM for every chunk that ends up RLE (rle_single_pass): run starts found with SIMD
-// byte compares, a decoupled look-back scan across the chunk's segments carrying (number of run
-// starts, position of the last run start), complete 5-byte records assembled in shared memory and
-// written with 16-byte stores.  A record is emitted
-// by the CTA in whose tile the run ENDS -- there both its length (this start minus the previous
-// start, which the scan carries across tiles however long the run was) and its value (the byte
-// before the new start) are known, so no second pass and no look-ahead are needed; the chunk's last
-// run is closed by the last tile.  Records go straight to their final place; a tile stops emitting
-// once the runs before it already make RLE impossible (5 * runs >= n).  Only a chunk that ends up
-// Raw takes a second kernel (raw_fixup), which copies the payload behind the header byte.
+// ONE pass over HBM for every chunk that ends up RLE (rle_tiles), one CTA per 8 KiB tile:
+//   1. the tile is loaded once (2 x 128-bit per thread), kept in shared memory, and its run starts are found
+//      with SWAR byte compares (one 32-bit mask per thread);
+//   2. a decoupled look-back over the chunk's tiles carries (number of run starts, position of the last
+//      run start): a tile publishes its aggregate as soon as it has counted and sums its predecessors'
+//      aggregates back to the nearest published inclusive prefix;
+//   3. the in-tile offsets of the run starts are appended to a list in shared memory;
+//   4. records are emitted by the tile in which a run ENDS -- there both its length (this start minus the
+//      previous start, which the scan carries across tiles however long the run was) and its value (the
+//      byte before the new start) are known, so no second pass and no look-ahead are needed; the chunk's
+//      last run is closed by the last tile.  The output is assembled 16 bytes at a time: a thread reads the
+//      five list entries behind its four records, builds the 20-byte record stream in registers with byte
+//      permutes and stores the aligned 16 bytes it owns straight to global memory (no staging, no byte
+//      stores except at the two ragged ends of the tile's output range).
+// A tile stops emitting once the runs before it already make RLE impossible (5 * runs >= n).  Only a chunk
+// that ends up Raw takes a second kernel (raw_fixup), which copies the payload behind the header byte.
 // Traffic: n read + serialised bytes written for RLE chunks (the algorithmic minimum).
+//
+// The file also compiles as plain C++ under tests/cuda_emul (MBC_EMULATE): a CPU execution of the very same
+// kernel text, one pthread per CUDA thread, which lets the index arithmetic be checked against the restated
+// serializer without a GPU (tests/test_codec_emulated.py).  The product never builds that way.
 #pragma once
 
+#ifdef MBC_EMULATE
+#include "cuda_emul.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace mbc {
 
 constexpr int kThreads = 256;
 constexpr int kHalf = 16;                              // one 128-bit load
-constexpr int kBytesPerThread = 2 * kHalf;             // two loads in flight per thread: 32 KiB per SM at 4 CTAs/SM
+constexpr int kBytesPerThread = 2 * kHalf;             // two loads in flight per thread
 constexpr int kTile = kThreads * kBytesPerThread;      // 8192 payload bytes per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kRound = 4096;                           // records assembled per round (a denser tile takes two rounds)
-constexpr int kStageRecBytes = 5 * kRound + 32;        // staging of one round's records (+ alignment slack)
-constexpr int kStageBytes = kStageRecBytes + 2 * (kTile + 8);   // ... followed by the tile's run-start offsets (uint16)
+// dynamic shared memory of rle_tiles: [15] the byte before the tile | [16, 16 + kTile) the tile |
+// uint16 list of the in-tile offsets of the run starts (+ the end-of-chunk sentinel on the last tile)
+constexpr int kCopyOff = 16;
+constexpr int kListOff = kCopyOff + kTile;
+constexpr int kSmemBytes = kListOff + 2 * (kTile + 8);
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -58,29 +74,38 @@ struct Batch {
     size_t payload_stride;
     uint8_t *out;                 // chunk c at out + c * out_stride (16-byte aligned stride)
     size_t out_stride;
-    TileStatus *status;           // per chunk: status + c * nsegs   (zeroed before every call)
+    TileStatus *status;           // per chunk: status + c * ntiles   (zeroed before every call)
+    uint32_t *dead;               // dead[c] != 0: some tile of chunk c has seen 5 * runs >= n, RLE is ruled out (zeroed likewise)
     Meta *meta;                   // meta[c]
-    size_t n;                     // payload bytes per chunk
+    size_t n;                     // payload bytes per chunk, < 2^32
     uint32_t ntiles;              // 8 KiB tiles per chunk
-    uint32_t seg_tiles;           // tiles per segment (one CTA of rle_single_pass)
-    uint32_t nsegs;               // segments per chunk
+    uint32_t n_chunks;
 };
 
-// 4-bit mask of the non-zero bytes of x (x = a ^ b: the bytes that differ), branch-free SWAR:
-// bit 7 of every non-zero byte, then the four bits gathered with one multiply
-__device__ __forceinline__ uint32_t nonzero4(uint32_t x)
+// bit 7 of every byte of `cur` that differs from the byte before it (`sh` = the same word one byte earlier)
+__device__ __forceinline__ uint32_t differ4(uint32_t cur, uint32_t sh)
 {
-    const uint32_t h = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
-    return (((h >> 7) * 0x01020408u) >> 24) & 0xfu;
+    const uint32_t x = cur ^ sh;
+    return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
 }
 
-// 16-bit mask of the run starts inside 16 payload bytes v, `prev` being the byte before them
-__device__ __forceinline__ uint32_t starts16(const uint4 &v, uint32_t prev)
+// appends the four flags of `h` (bits 7, 15, 23, 31) as a nibble below the nibbles already in `mask`: the
+// multiply gathers them in bits 28..31 (the ten partial products land on ten different bits, no carries)
+__device__ __forceinline__ uint32_t push4(uint32_t mask, uint32_t h)
 {
-    // the same 16 bytes shifted up by one byte, `prev` entering at the bottom
-    const uint32_t s0 = __byte_perm(prev, v.x, 0x6540), s1 = __byte_perm(v.x, v.y, 0x6543);
-    const uint32_t s2 = __byte_perm(v.y, v.z, 0x6543), s3 = __byte_perm(v.z, v.w, 0x6543);
-    return nonzero4(v.x ^ s0) | (nonzero4(v.y ^ s1) << 4) | (nonzero4(v.z ^ s2) << 8) | (nonzero4(v.w ^ s3) << 12);
+    return __funnelshift_l(h * 0x00204081u, mask, 4);
+}
+
+// index of the highest set bit of m != 0 (one FLO)
+__device__ __forceinline__ uint32_t top_bit(uint32_t m)
+{
+#ifdef MBC_EMULATE
+    return 31u - (uint32_t)__clz(m);
+#else
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m));
+    return r;
+#endif
 }
 
 // 32-bit mask: bit j set iff byte j of this thread's 32-byte span starts a run (p[i] != p[i-1];
@@ -92,7 +117,16 @@ __device__ __forceinline__ uint32_t span_mask_fast(const uint8_t *__restrict__ p
     v1 = *reinterpret_cast<const uint4 *>(p + base + kHalf);
     prev = __shfl_up_sync(0xffffffffu, v1.w >> 24, 1);
     if ((threadIdx.x & 31) == 0) prev = base ? (uint32_t)p[base - 1] : 0u;
-    uint32_t mask = starts16(v0, prev) | (starts16(v1, v0.w >> 24) << kHalf);
+    // nibbles are pushed from the last word to the first, so that word 0 ends up in bits 0..3
+    uint32_t mask = 0;
+    mask = push4(mask, differ4(v1.w, __byte_perm(v1.z, v1.w, 0x6543)));
+    mask = push4(mask, differ4(v1.z, __byte_perm(v1.y, v1.z, 0x6543)));
+    mask = push4(mask, differ4(v1.y, __byte_perm(v1.x, v1.y, 0x6543)));
+    mask = push4(mask, differ4(v1.x, __byte_perm(v0.w, v1.x, 0x6543)));
+    mask = push4(mask, differ4(v0.w, __byte_perm(v0.z, v0.w, 0x6543)));
+    mask = push4(mask, differ4(v0.z, __byte_perm(v0.y, v0.z, 0x6543)));
+    mask = push4(mask, differ4(v0.y, __byte_perm(v0.x, v0.y, 0x6543)));
+    mask = push4(mask, differ4(v0.x, __byte_perm(prev, v0.x, 0x6540)));
     if (base == 0) mask |= 1u;
     return mask;
 }
@@ -130,248 +164,208 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
 }
 
-// CTA-wide (sum, max) of a per-thread pair; every thread receives the totals
-__device__ __forceinline__ void block_sum_max(uint32_t c, uint32_t l, uint32_t *w_cnt, uint32_t *w_last, uint32_t &tot, uint32_t &totlast)
+// one look-back status: flag 0 while the two words are unpublished or belong to different publications
+__device__ __forceinline__ void ld_pair(const TileStatus *st, uint32_t &flag, uint32_t &count, uint32_t &last)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-        const uint32_t l2 = __shfl_xor_sync(0xffffffffu, l, o);
-        l = l > l2 ? l : l2;
-    }
-    __syncthreads();                       // the arrays may still be read by the previous user
-    if (lane == 0) { w_cnt[warp] = c; w_last[warp] = l; }
-    __syncthreads();
-    tot = 0;
-    totlast = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        tot += w_cnt[w];
-        totlast = totlast > w_last[w] ? totlast : w_last[w];
-    }
+    const unsigned long long sc = ld_status(&st->count), sl = ld_status(&st->last);
+    const uint32_t fc = (uint32_t)(sc >> 62), fl = (uint32_t)(sl >> 62);
+    flag = fc == fl ? fc : 0u;
+    count = (uint32_t)sc;                                      // run counts and positions are below 2^32
+    last = (uint32_t)sl;
 }
 
-// The single pass.  grid = (segments, n_chunks), kThreads threads, kStageBytes of dynamic shared memory.
-// A CTA owns a SEGMENT of b.seg_tiles consecutive 8 KiB tiles:
-//   phase 1  streams the segment once from HBM and counts its run starts (+ position of the last one);
-//   look-back  one decoupled look-back per SEGMENT (a few hundred per chunk, not thousands of tiles:
-//            the chain is short and several chunks are in flight at once);
-//   phase 2  walks the segment's tiles again -- now L2 hits, the segment was just read -- and emits the
-//            records, carrying the running (runs, last start) in shared memory from tile to tile.
-// Segment ids follow blockIdx.x: blocks are dispatched in increasing linear index, so every
-// predecessor a segment waits for is running or done (the usual decoupled-look-back assumption).
-__global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
+// Decoupled look-back, executed by one whole warp of tile `tile` >= 1: sums the predecessors' aggregates back
+// to the nearest published inclusive prefix.  Returns (1 + position of the last run start before this tile) << 32 |
+// (run starts before it) in every lane.  A tile publishes its aggregate before it waits for anybody, and the
+// blocks of a chunk are dispatched in increasing tile order, so every predecessor a tile waits for is running or
+// done (the usual decoupled-look-back assumption).  One round trip to L2 inspects kLook * 32 predecessors: the
+// front of inclusive prefixes advances by that many tiles per round trip, which is what bounds a single chunk.
+constexpr int kLook = 4;
+__device__ __noinline__ unsigned long long look_back(const TileStatus *status, uint32_t tile, uint32_t lane)
 {
-    extern __shared__ __align__(16) uint8_t stage[];
-    __shared__ uint32_t w_cnt[kWarps], w_last[kWarps];
-    __shared__ uint32_t s_runs_before, s_last_before;
-
-    const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
-    uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
-    TileStatus *status = b.status + (size_t)blockIdx.y * b.nsegs;
-    const size_t n = b.n;
-    const uint32_t seg = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile0 = seg * b.seg_tiles;
-    const uint32_t ntl = b.ntiles - tile0 < b.seg_tiles ? b.ntiles - tile0 : b.seg_tiles;
-
-    // a tile is `regular` when all of it lies inside the payload and the payload is 16-byte aligned
-    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
-
-    // ---- phase 1: run starts of the whole segment --------------------------------------------------
-    uint32_t seg_cnt = 0, seg_last = 0;
-    uint32_t busy = 0;                                   // bit k: my span of tile k holds a run start
-    // regular tiles first, unrolled so that several 128-bit loads per thread are in flight (this loop is
-    // the HBM stream of the kernel); a ragged last tile / unaligned payload takes the general path
-    uint32_t nreg = 0;
-    if (aligned) {
-        const size_t whole = n / kTile;                  // tiles that lie completely inside the payload
-        nreg = whole > tile0 ? (uint32_t)(whole - tile0 < ntl ? whole - tile0 : ntl) : 0u;
-    }
-#pragma unroll 4
-    for (uint32_t k = 0; k < nreg; ++k) {
-        uint4 v0, v1;
-        uint32_t pv;
-        const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        const uint32_t m = span_mask_fast(p, base, v0, v1, pv);
-        if (m) {
-            seg_cnt += __popc(m);
-            seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;                // positions grow with k
-            busy |= 1u << k;
-        }
-    }
-    for (uint32_t k = nreg; k < ntl; ++k) {
-        uint4 v0, v1;
-        uint32_t pv;
-        const size_t base = (size_t)(tile0 + k) * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        const uint32_t m = span_mask_slow(p, base, n, v0, v1, pv);
-        if (m) {
-            seg_cnt += __popc(m);
-            seg_last = (uint32_t)base + (31u - __clz(m)) + 1u;
-            busy |= 1u << k;
-        }
-    }
-    uint32_t seg_tot, seg_totlast;
-    block_sum_max(seg_cnt, seg_last, w_cnt, w_last, seg_tot, seg_totlast);
-
-    // ---- decoupled look-back over segments: (runs before this segment, last start before it) -------
-    if (warp == 0) {
-        unsigned long long runs_before = 0, last_before = 0;
-        if (seg == 0) {
-            if (lane == 0) {
-                st_status(&status[0].count, kFlagInclusive | seg_tot);
-                st_status(&status[0].last, kFlagInclusive | seg_totlast);
-            }
-        } else {
-            if (lane == 0) {
-                st_status(&status[seg].count, kFlagAggregate | seg_tot);
-                st_status(&status[seg].last, kFlagAggregate | seg_totlast);
-            }
-            int look = (int)seg - 1;                               // lane k inspects segment look - k
-            for (;;) {
-                const int t = look - (int)lane;
-                unsigned long long sc = kFlagInclusive, sl = kFlagInclusive;     // "before segment 0": empty inclusive prefix
-                if (t >= 0) {
-                    do {
-                        sc = ld_status(&status[t].count);
-                        sl = ld_status(&status[t].last);
-                    } while ((sc & kFlagMask) == 0 || (sc & kFlagMask) != (sl & kFlagMask));
-                }
-                const bool inclusive = (sc & kFlagMask) == kFlagInclusive;
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, inclusive);
-                // use the window up to and including the nearest inclusive prefix
-                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
-                unsigned long long c = (int)lane <= stop ? (sc & ~kFlagMask) : 0ull;
-                unsigned long long l = (int)lane <= stop ? (sl & ~kFlagMask) : 0ull;
+    uint32_t rb = 0, lb = 0;
+    int look = (int)tile - 1;                                  // lane l inspects tiles look - l - 32 k, k = 0 .. kLook - 1
+    for (;;) {
+        uint32_t flag[kLook], cv[kLook], lv[kLook];            // 0 = not published yet (or a torn pair), 1 aggregate, 2 inclusive
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    c += __shfl_down_sync(0xffffffffu, c, o);
-                    const unsigned long long l2 = __shfl_down_sync(0xffffffffu, l, o);
-                    l = l > l2 ? l : l2;
+        for (int k = 0; k < kLook; ++k) {                      // all loads of the round are in flight together
+            const int t = look - (int)lane - 32 * k;
+            flag[k] = 2u;                                      // "before tile 0": empty inclusive prefix
+            cv[k] = 0u;
+            lv[k] = 0u;
+            if (t >= 0) ld_pair(&status[t], flag[k], cv[k], lv[k]);
+        }
+        uint32_t c = 0, l = 0;
+        bool found = false;                                    // an inclusive prefix among the nearer statuses (warp-uniform)
+#pragma unroll
+        for (int k = 0; k < kLook; ++k) {
+            if (!found) {                                      // statuses beyond the nearest inclusive prefix are not needed
+                const int t = look - (int)lane - 32 * k;
+                while (flag[k] == 0u) ld_pair(&status[t], flag[k], cv[k], lv[k]);
+                const unsigned incl = __ballot_sync(0xffffffffu, flag[k] == 2u);
+                // use the window up to and including the nearest inclusive prefix
+                const uint32_t stop = incl ? (uint32_t)__ffs(incl) - 1u : 31u;
+                if (lane <= stop) {
+                    c += cv[k];
+                    l = l > lv[k] ? l : lv[k];
                 }
-                c = __shfl_sync(0xffffffffu, c, 0);
-                l = __shfl_sync(0xffffffffu, l, 0);
-                runs_before += c;
-                last_before = last_before > l ? last_before : l;
-                if (incl_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) {
-                const unsigned long long li = seg_totlast ? (unsigned long long)seg_totlast : last_before;
-                st_status(&status[seg].count, kFlagInclusive | (runs_before + seg_tot));
-                st_status(&status[seg].last, kFlagInclusive | li);
+                found = incl != 0;
             }
         }
-        if (lane == 0) { s_runs_before = (uint32_t)runs_before; s_last_before = (uint32_t)last_before; }
+        rb += __reduce_add_sync(0xffffffffu, c);
+        const uint32_t lm = __reduce_max_sync(0xffffffffu, l);
+        lb = lb > lm ? lb : lm;
+        if (found) break;
+        look -= 32 * kLook;
     }
-    __syncthreads();
-    const bool last_seg = (seg + 1 == b.nsegs);
-    uint32_t runs_before = s_runs_before, last_before = s_last_before;        // carried in registers, identical in every thread
-    const uint32_t runs_total = runs_before + seg_tot;                        // the chunk's run count, on the last segment
+    return ((unsigned long long)lb << 32) | rb;                // a call, not inlined: its registers stay out of the kernel's budget
+}
 
-    // ---- phase 2: records of the runs that END in each tile of the segment -------------------------
-    // run (g - 1) for every start with global index g >= 1, plus the chunk's last run on its last tile.
-    // Record r lives at out[1 + 5r .. 1 + 5r + 5).  Tiles from which on RLE is already ruled out
-    // (5 * runs >= n keeps Raw, and runs only grow) are skipped, and so are tiles without a run start.
-    for (uint32_t k = 0; k < ntl; ++k) {
-        if ((unsigned long long)runs_before * 5ull >= (unsigned long long)n) break;
-        const uint32_t tile = tile0 + k;
-        const bool is_last_tile = (tile + 1 == b.ntiles);
-        // also the barrier that releases the staging buffer and w_* of the previous tile
-        if (!__syncthreads_or((busy >> k) & 1u) && !is_last_tile) continue;
+// byte s of the record stream of a tile (records of the runs that end in it, back to back): the general form,
+// used for the few bytes at the two ends of the tile's output range that do not fill an aligned 16-byte word
+__device__ __forceinline__ uint32_t stream_byte(uint32_t s, uint32_t skip, uint32_t before, const uint16_t *s_pos, const uint8_t *cp)
+{
+    const uint32_t r = s / 5u, f = s - 5u * r, e = r + skip;
+    const uint32_t pos = s_pos[e];
+    const uint32_t pm = e ? (uint32_t)s_pos[e - 1] : before;
+    const uint32_t len = pos - pm;                                     // BitConverter.GetBytes(runLength): little-endian
+    return f < 4u ? (len >> (8u * f)) & 0xffu : (uint32_t)cp[pos];    // runValue (DataChunkSerializer.cs:84,98)
+}
+
+// The single pass.  grid = tiles * n_chunks blocks in chunk-minor order (block id = tile * n_chunks + chunk): the
+// blocks in flight at any time belong to all chunks of the batch, so that as many look-back fronts advance side
+// by side.  kThreads threads, kSmemBytes of dynamic shared memory.
+__global__ void __launch_bounds__(kThreads, 6) rle_tiles(const Batch b)
+{
+#ifdef MBC_EMULATE
+    uint8_t *smem = EMUL_DYNAMIC_SMEM;
+#else
+    extern __shared__ __align__(16) uint8_t smem[];
+#endif
+    __shared__ uint32_t w_cnt[kWarps], w_last[kWarps];
+    __shared__ uint32_t s_runs_before, s_last_before, s_ruled_out;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x / b.n_chunks, chunk = blockIdx.x - tile * b.n_chunks;
+    const uint8_t *__restrict__ p = b.payloads + chunk * b.payload_stride;
+    uint8_t *__restrict__ out = b.out + chunk * b.out_stride;
+    TileStatus *status = b.status + (size_t)chunk * b.ntiles;
+    const uint32_t n = (uint32_t)b.n;
+    const uint32_t tile_base = tile * (uint32_t)kTile;                 // < n
+    const uint32_t span = tid * (uint32_t)kBytesPerThread;             // in-tile offset of my 32 bytes
+    const bool is_last_tile = tile + 1u == b.ntiles;
+    // a tile is `regular` when all of it lies inside the payload and the payload is 16-byte aligned
+    const bool regular = (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && n - tile_base >= (uint32_t)kTile;
+
+    // ---- 1. the tile, once: run-start mask of my span, the bytes themselves go to shared memory ----------
+    uint32_t mask;
+    {
         uint4 v0, v1;
         uint32_t prev;
-        const size_t base = (size_t)tile * kTile + (size_t)threadIdx.x * kBytesPerThread;
-        const bool regular = aligned && (size_t)(tile + 1) * kTile <= n;
-        uint32_t mask = regular ? span_mask_fast(p, base, v0, v1, prev) : span_mask_slow(p, base, n, v0, v1, prev);   // L2 hits
-        const uint32_t cnt = __popc(mask);
-        const uint32_t mylast = cnt ? (uint32_t)base + (31u - __clz(mask)) + 1u : 0u;
-        // CTA-wide scan of (count, last start): inclusive in the warp, then across warps
-        uint32_t inc = cnt, lastinc = mylast;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t c = __shfl_up_sync(0xffffffffu, inc, o), l = __shfl_up_sync(0xffffffffu, lastinc, o);
-            if (lane >= (uint32_t)o) { inc += c; lastinc = lastinc > l ? lastinc : l; }
-        }
-        if (lane == 31) { w_cnt[warp] = inc; w_last[warp] = lastinc; }
-        __syncthreads();
-        uint32_t wbase = 0, tot = 0, totlast = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = w_cnt[w], l = w_last[w];
-            if ((uint32_t)w < warp) wbase += c;
-            tot += c;
-            totlast = totlast > l ? totlast : l;
-        }
-        const uint32_t rank = wbase + inc - cnt;                       // starts of this tile before my span
+        const size_t base = (size_t)tile_base + span;
+        mask = regular ? span_mask_fast(p, base, v0, v1, prev) : span_mask_slow(p, base, n, v0, v1, prev);
+        *reinterpret_cast<uint4 *>(smem + kCopyOff + span) = v0;
+        *reinterpret_cast<uint4 *>(smem + kCopyOff + span + kHalf) = v1;
+        if (tid == 0) smem[kCopyOff - 1] = (uint8_t)prev;
+    }
+    const uint32_t cnt = __popc(mask);
+    const uint32_t mylast = cnt ? span + 32u - (uint32_t)__clz(mask) : 0u;      // 1 + in-tile offset of my last start
 
-        // a) every thread appends the in-tile offsets of its run starts to a list (a short divergent loop:
-        //    runs cluster, a lane may hold ten starts while its neighbours hold none)
-        uint16_t *s_pos = reinterpret_cast<uint16_t *>(stage + kStageRecBytes);
-        {
-            uint32_t e = rank;
-            const uint32_t off = threadIdx.x * kBytesPerThread;
-            while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                s_pos[e++] = (uint16_t)(off + j);
-            }
+    // CTA-wide exclusive scan of the counts, total, and the last start of the tile
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t c = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += c;
+    }
+    const uint32_t wl = __reduce_max_sync(0xffffffffu, mylast);
+    if (lane == 31) w_cnt[warp] = inc;
+    if (lane == 0) w_last[warp] = wl;
+    // RLE already ruled out by an earlier tile?  (a hint, read once per CTA so that all threads agree; a stale 0
+    // only costs the work, and whoever set it saw 5 * runs >= n, so the chunk ends up Raw whatever is skipped)
+    if (tid == 0) s_ruled_out = *reinterpret_cast<const volatile uint32_t *>(b.dead + chunk);
+    __syncthreads();
+    // the eight warp totals are scanned by the first eight lanes of every warp
+    uint32_t wsum = lane < (uint32_t)kWarps ? w_cnt[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < kWarps; o <<= 1) {
+        const uint32_t c = __shfl_up_sync(0xffffffffu, wsum, o);
+        if (lane >= (uint32_t)o) wsum += c;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, wsum, kWarps - 1);
+    const uint32_t wbase = __shfl_sync(0xffffffffu, wsum, warp) - w_cnt[warp];
+    const uint32_t totlast = __reduce_max_sync(0xffffffffu, lane < (uint32_t)kWarps ? w_last[lane] : 0u);
+    const uint32_t rank = wbase + inc - cnt;                           // starts of this tile before my span
+    const unsigned long long agg_last = totlast ? (unsigned long long)tile_base + totlast : 0ull;   // 1 + position in the chunk
+
+    // ---- 2. publish the aggregate at once (tile 0: its inclusive prefix) ---------------------------------
+    if (tid == 0) {
+        const unsigned long long flag = tile ? kFlagAggregate : kFlagInclusive;
+        st_status(&status[tile].count, flag | tot);
+        st_status(&status[tile].last, flag | agg_last);
+    }
+    // a tile without a run start closes no run (unless it is the last one): it only passes the prefix on; so does
+    // a tile that found RLE ruled out
+    const bool emits = (tot != 0 && s_ruled_out == 0) || is_last_tile;
+
+    // ---- 3. the list of run-start offsets (does not need the prefix: predecessors get time to publish) ----
+    uint16_t *s_pos = reinterpret_cast<uint16_t *>(smem + kListOff);
+    if (emits) {
+        // filled from the top (the highest set bit is one FLO away), four entries per trip
+        uint16_t *q = s_pos + rank + cnt;
+        uint32_t m = mask;
+#pragma unroll 1
+        while (m) {                                                    // a short divergent loop: runs cluster
+            uint32_t j = top_bit(m);
+            q[-1] = (uint16_t)(span + j);
+            m ^= 1u << j;
+            if (!m) break;
+            j = top_bit(m);
+            q[-2] = (uint16_t)(span + j);
+            m ^= 1u << j;
+            if (!m) break;
+            j = top_bit(m);
+            q[-3] = (uint16_t)(span + j);
+            m ^= 1u << j;
+            if (!m) break;
+            j = top_bit(m);
+            q[-4] = (uint16_t)(span + j);
+            m ^= 1u << j;
+            q -= 4;
         }
-        __syncthreads();
-        // b) the list is turned into records by ALL threads, one list entry each (balanced, no divergence):
-        //    entry e is the start with global index g = runs_before + e and closes run g - 1, whose length
-        //    is this start minus the previous one and whose value is the byte before this start
-        const size_t tile_base = (size_t)tile * kTile;
-        const uint32_t skip = runs_before ? 0u : 1u;                               // start 0 of the chunk closes nothing
-        const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;           // first record this tile writes
-        const uint32_t n_rec = (tot > skip ? tot - skip : 0u) + (is_last_tile ? 1u : 0u);
-        for (uint32_t r0 = 0; r0 < n_rec; r0 += kRound) {
-            const uint32_t r1 = r0 + kRound < n_rec ? r0 + kRound : n_rec;        // records [r0, r1) of this tile in this round
-            const size_t out_lo = 1 + ((size_t)first_rec + r0) * 5;               // their byte range in the output
-            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + out_lo) & 15u);   // stage congruent to out mod 16
-            for (uint32_t r = r0 + threadIdx.x; r < r1; r += kThreads) {
-                uint32_t len, val;
-                const uint32_t e = r + skip;                                       // list entry that closes record r
-                if (e < tot) {
-                    const uint32_t pos = (uint32_t)tile_base + s_pos[e];
-                    const uint32_t before = e ? (uint32_t)tile_base + s_pos[e - 1] : last_before - 1u;
-                    len = pos - before;                                            // BitConverter.GetBytes(runLength): little-endian
-                    val = p[pos - 1];                                              // runValue (DataChunkSerializer.cs:84,98): an L1/L2 hit
-                } else {
-                    // the chunk's last run: from the last start anywhere to n
-                    const uint32_t last_start = (totlast ? totlast : last_before) - 1u;
-                    len = (uint32_t)n - last_start;
-                    val = p[n - 1];
-                }
-                uint8_t *rec = stage + shift + (size_t)(r - r0) * 5;
-                rec[0] = (uint8_t)len;
-                rec[1] = (uint8_t)(len >> 8);
-                rec[2] = (uint8_t)(len >> 16);
-                rec[3] = (uint8_t)(len >> 24);
-                rec[4] = (uint8_t)val;
-            }
-            __syncthreads();
-            // copy out: bytes beyond n can never be part of an RLE result (5 * runs < n) and are dropped
-            size_t nbytes = (size_t)(r1 - r0) * 5;
-            if (out_lo + nbytes > n + 1) nbytes = out_lo < n + 1 ? n + 1 - out_lo : 0;
-            uint8_t *dst = out + out_lo;
-            const uint8_t *src = stage + shift;
-            const size_t head = nbytes < ((16u - shift) & 15u) ? nbytes : ((16u - shift) & 15u);
-            for (size_t q = threadIdx.x; q < head; q += kThreads) dst[q] = src[q];                 // up to the first 16-byte boundary
-            const size_t body = (nbytes - head) / 16;
-            for (size_t q = threadIdx.x; q < body; q += kThreads)
-                reinterpret_cast<uint4 *>(dst + head)[q] = reinterpret_cast<const uint4 *>(src + head)[q];
-            for (size_t q = head + body * 16 + threadIdx.x; q < nbytes; q += kThreads) dst[q] = src[q];
-            if (r1 < n_rec) __syncthreads();                                       // the next round reuses the staging area
-        }
-        runs_before += tot;                                                        // carry the prefix to the next tile
-        if (totlast) last_before = totlast;
+        // the end of the chunk closes its last run like one more start would
+        if (is_last_tile && tid == 0) s_pos[tot] = (uint16_t)(n - tile_base);
     }
 
-    // the last segment knows the run count: pick the codec, write header + length + classification
-    if (last_seg && threadIdx.x == 0) {
-        Meta *meta = b.meta + blockIdx.y;
-        const uint32_t runs = runs_total;
+    // ---- look-back by warp 0, inclusive prefix published for the successors ------------------------------
+    if (warp == 0) {
+        uint32_t rb = 0, lb = 0;
+        if (tile) {
+            const unsigned long long r = look_back(status, tile, lane);
+            rb = (uint32_t)r;
+            lb = (uint32_t)(r >> 32);
+            if (lane == 0) {
+#ifdef MBC_EMULATE
+                // the emulator runs the CTAs one after the other, so every predecessor would be inclusive:
+                // leave most tiles at their aggregate to exercise the summation over several windows
+                if (!mbc_emul_keep_aggregate(tile))
+#endif
+                {
+                    st_status(&status[tile].count, kFlagInclusive | ((unsigned long long)rb + tot));
+                    st_status(&status[tile].last, kFlagInclusive | (agg_last ? agg_last : (unsigned long long)lb));
+                }
+            }
+        }
+        if (lane == 0) { s_runs_before = rb; s_last_before = lb; }
+    }
+    if (!emits) return;                                                // uniform: nobody is left behind at the barrier
+    __syncthreads();
+    const uint32_t runs_before = s_runs_before, last_before = s_last_before;
+
+    // the last tile knows the run count: pick the codec, write header + length + classification
+    if (is_last_tile && tid == 0) {
+        Meta *meta = b.meta + chunk;
+        const uint32_t runs = runs_before + tot;
         // DataChunk.cs:181-204: the first serializer (Raw) is kept unless RLE is strictly shorter
         const bool rle = (unsigned long long)runs * 5ull < (unsigned long long)n;
         meta->runs = runs;
@@ -379,10 +373,66 @@ __global__ void __launch_bounds__(kThreads, 4) rle_single_pass(const Batch b)
         meta->out_len = 1ull + (rle ? (unsigned long long)runs * 5ull : (unsigned long long)n);
         // one run of 0s = IsNeverChunk, one run of 1s = IsImmediateChunk (DataChunk.cs:82,87);
         // Never is tested first (DataStorage.cs:74-77) but the two cannot both hold
-        const uint32_t v0 = p[0];
-        meta->first_value = v0;
-        meta->entry_type = (runs == 1 && v0 == 0) ? 1u : (runs == 1 && v0 == 1) ? 2u : 0u;
+        const uint32_t first = p[0];
+        meta->first_value = first;
+        meta->entry_type = (runs == 1 && first == 0) ? 1u : (runs == 1 && first == 1) ? 2u : 0u;
         out[0] = rle ? 0x01 : 0x00;        // Serializer.SerializeCode, DataChunkSerializer.cs:20-23
+    }
+
+    // ---- 4. records of the runs that END in this tile ----------------------------------------------------
+    // List entry e (e = 0 .. tot-1, plus the sentinel e = tot on the last tile) is the start with global index
+    // g = runs_before + e and closes run g - 1: length = this start minus the previous one, value = the byte
+    // before this start.  Record r lives at out[1 + 5r .. 1 + 5r + 5).  Once the runs before the tile make
+    // RLE impossible (5 * runs >= n keeps Raw, and runs only grow) nothing is emitted any more.
+    if ((unsigned long long)runs_before * 5ull >= (unsigned long long)n) {
+        if (tid == 0) *reinterpret_cast<volatile uint32_t *>(b.dead + chunk) = 1u;
+        return;
+    }
+    const uint32_t skip = runs_before ? 0u : 1u;                       // start 0 of the chunk closes nothing
+    const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;    // first record this tile writes
+    const uint32_t n_ent = tot + (is_last_tile ? 1u : 0u);
+    const uint32_t n_rec = n_ent - skip;                               // tile 0 holds start 0, so n_ent >= skip
+    const unsigned long long out_lo = 1ull + 5ull * first_rec;         // <= n: the tile's record stream starts here
+    uint32_t slen = 5u * n_rec;                                        // ... and is this long;
+    if ((unsigned long long)slen > (unsigned long long)n + 1ull - out_lo)
+        slen = (uint32_t)((unsigned long long)n + 1ull - out_lo);      // bytes beyond n + 1 can never be part of an RLE result
+    uint8_t *dst = out + out_lo;
+    const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const uint32_t before = last_before - 1u - tile_base;              // in-tile offset of the start before entry 0 (wraps below 0)
+    const uint8_t *cp = smem + kCopyOff - 1;                           // cp[o] = the byte before in-tile offset o
+    // aligned words that lie completely inside the stream: word q covers stream bytes [16q - shift, 16q - shift + 16)
+    const uint32_t q_first = shift ? 1u : 0u, q_end = (shift + slen) >> 4;
+    for (uint32_t q = q_first + tid; q < q_end; q += kThreads) {
+        const uint32_t s0 = 16u * q - shift;
+        const uint32_t ra = s0 / 5u, phase = s0 - 5u * ra;             // first record of the word, and where the word starts in it
+        const uint32_t ea = ra + skip;
+        const uint16_t *e = s_pos + ea;
+        uint32_t pm = e[-1];                                           // (e = 0: the two bytes before the list, in bounds, unused)
+        if (ea == 0) pm = before;
+        const uint32_t p0 = e[0], p1 = e[1], p2 = e[2], p3 = e[3];     // a whole word always touches four records
+        const uint32_t l0 = p0 - pm, l1 = p1 - p0, l2 = p2 - p1, l3 = p3 - p2;
+        const uint32_t c0 = cp[p0], c1 = cp[p1], c2 = cp[p2], c3 = cp[p3];
+        // the 20 bytes of the four records: l0 | c0 l1[0..2] | l1[3] c1 l2[0..1] | l2[2..3] c2 l3[0] | l3[1..3] c3
+        const uint32_t w0 = l0;
+        const uint32_t w1 = __byte_perm(c0, l1, 0x6540);
+        const uint32_t w2 = __byte_perm(__byte_perm(l1, c1, 0x0043), l2, 0x5410);
+        const uint32_t w3 = __byte_perm(__byte_perm(l2, c2, 0x0432), l3, 0x4210);
+        const uint32_t w4 = __byte_perm(l3, c3, 0x4321);
+        const uint32_t sel = 0x3210u + 0x1111u * phase;                // bytes phase .. phase + 3 of a word pair
+        uint4 w;
+        w.x = __byte_perm(w0, w1, sel);
+        w.y = __byte_perm(w1, w2, sel);
+        w.z = __byte_perm(w2, w3, sel);
+        w.w = __byte_perm(w3, w4, sel);
+        *reinterpret_cast<uint4 *>(dst + s0) = w;
+    }
+    // the bytes before the first and after the last whole word (< 16 each; < 32 when there is no whole word)
+    if (warp == kWarps - 1) {
+        const bool any = q_end > q_first;
+        const uint32_t head_end = any ? 16u * q_first - shift : slen;
+        const uint32_t tail_lo = any ? 16u * q_end - shift : slen;
+        if (lane < head_end) dst[lane] = (uint8_t)stream_byte(lane, skip, before, s_pos, cp);
+        if (tail_lo + lane < slen) dst[tail_lo + lane] = (uint8_t)stream_byte(tail_lo + lane, skip, before, s_pos, cp);
     }
 }
 

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "chunk_codec.cuh"
+#include "chunk_codec_segments.cuh"   // DEV-ONLY A/B (MB_CODEC_SEGMENTS=1)
 #include "escape_kernels.cuh"
 #include "escape_refill.cuh"
 
@@ -982,8 +983,8 @@ size_t mb_serialize_out_stride(size_t n) { return round_up(n + 1, 256); }
 
 size_t mb_serialize_workspace_bytes(size_t n, uint32_t n_chunks)
 {
-    // per chunk: one 16-byte look-back status per segment (at most one per 8 KiB tile)
-    return 256 + (size_t)n_chunks * sizeof(mbc::TileStatus) * codec_tiles(n);
+    // per chunk: one 16-byte look-back status per 8 KiB tile, and a 4-byte "RLE ruled out" hint
+    return 256 + round_up((size_t)n_chunks * (sizeof(mbc::TileStatus) * codec_tiles(n) + sizeof(uint32_t)), 256);
 }
 
 int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks, size_t payload_stride, uint8_t *out_dev,
@@ -1001,6 +1002,29 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     int rc = current_ctx(&c);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool use_segments = getenv("MB_CODEC_SEGMENTS") && atoi(getenv("MB_CODEC_SEGMENTS")) != 0;   // DEV-ONLY A/B
+    if (use_segments) {
+        mbc_seg::Batch b;
+        b.payloads = payloads_dev;
+        b.payload_stride = payload_stride;
+        b.out = out_dev;
+        b.out_stride = out_stride;
+        b.status = reinterpret_cast<mbc_seg::TileStatus *>(static_cast<uint8_t *>(workspace_dev) + 256);
+        b.meta = reinterpret_cast<mbc_seg::Meta *>(info_dev);
+        b.n = n;
+        b.ntiles = (uint32_t)codec_tiles(n);
+        const uint64_t want_ctas = (uint64_t)c->sm_count * 4;
+        uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
+        if (seg < 1) seg = 1;
+        if (seg > 16) seg = 16;
+        b.seg_tiles = (uint32_t)seg;
+        b.nsegs = (b.ntiles + b.seg_tiles - 1) / b.seg_tiles;
+        MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.nsegs * sizeof(mbc_seg::TileStatus), st));
+        mbc_seg::rle_single_pass<<<dim3(b.nsegs, n_chunks, 1), mbc_seg::kThreads, mbc_seg::kStageBytes, st>>>(b);
+        mbc_seg::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc_seg::kThreads, 0, st>>>(b);
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
     mbc::Batch b;
     b.payloads = payloads_dev;
     b.payload_stride = payload_stride;
@@ -1010,17 +1034,12 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
     b.n = n;
     b.ntiles = (uint32_t)codec_tiles(n);
-    // segment length: long segments keep the look-back chain short (one dependent L2 round trip per 32
-    // predecessors) and let phase 2 re-read from L2; a single 16 MiB chunk still gets ~500 CTAs (one wave)
-    const uint64_t want_ctas = (uint64_t)c->sm_count * 4;
-    uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
-    if (seg < 1) seg = 1;
-    if (seg > 16) seg = 16;                                                       // 128 KiB per CTA; 8 was tried: run-dense chunks +1.5 %, constant chunks -16 % (longer look-back chain)
-    b.seg_tiles = (uint32_t)seg;
-    b.nsegs = (b.ntiles + b.seg_tiles - 1) / b.seg_tiles;
-    // the look-back flags must start out invalid
-    MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.nsegs * sizeof(mbc::TileStatus), st));
-    mbc::rle_single_pass<<<dim3(b.nsegs, n_chunks, 1), mbc::kThreads, mbc::kStageBytes, st>>>(b);   // everything, for chunks that end up RLE
+    b.n_chunks = n_chunks;
+    b.dead = reinterpret_cast<uint32_t *>(b.status + (size_t)n_chunks * b.ntiles);
+    // the look-back flags must start out invalid, the hints clear
+    MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * (b.ntiles * sizeof(mbc::TileStatus) + sizeof(uint32_t)), st));
+    // chunk-minor block order: tiles * n_chunks <= 2^19 * 2^16 < 2^31 - 1 blocks
+    mbc::rle_tiles<<<b.ntiles * n_chunks, mbc::kThreads, mbc::kSmemBytes, st>>>(b);   // everything, for chunks that end up RLE
     mbc::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc::kThreads, 0, st>>>(b);     // exits at once unless the chunk ended up Raw
     MB_CUDA(cudaGetLastError());
     return MB_OK;

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--only", default=None, help="substring of the case name (for ncu captures)")
 ap.add_argument("--nb", type=int, nargs="*", default=[1, 64])
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--out", default="codec_bench.json", help="file name under gpurun_out/")
 args = ap.parse_args()
 nat.init(0)
 L = nat.lib()
@@ -61,4 +62,4 @@ for nb in args.nb:
                              "ms_median": ms, "us_per_chunk": ms * 1e3 / nb, "algorithmic_gb_s": gbs, "frac_of_hbm_peak": gbs / hbm})
         print(res["cases"][-1], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "codec_bench.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", args.out), "w"), indent=1)

@@ -1,0 +1,199 @@
+// cuda_emul.h -- TEST INFRASTRUCTURE: runs the text of a CUDA kernel on the CPU, one pthread per CUDA thread of a
+// CTA, CTAs one after the other in dispatch order (blockIdx.x fastest).  Just enough of the CUDA surface for
+// distributedmandelbrot_b200/csrc/chunk_codec.cuh: thread/block indices, __syncthreads, the warp shuffles / votes /
+// reductions the kernel uses, the integer intrinsics, uint4.  It exists so that the index arithmetic of the device
+// serializer can be checked against the restated reference serializer in a container without a GPU
+// (tests/test_codec_emulated.py).  Never part of the product build; nothing here is timed.
+//
+// Semantics kept: all threads of a CTA run concurrently and meet at barriers; __shared__ variables are one per CTA
+// (CTAs are sequential, so a function-level static does it); warp collectives exchange through a per-warp slot array
+// between two warp barriers.  Not modelled: the memory model (everything is sequentially consistent enough through
+// the barriers), divergence inside a warp collective (the kernel never does that), more than one CTA in flight.
+#pragma once
+
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+struct emul_uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+extern thread_local emul_uint3 threadIdx, blockIdx;
+extern emul_uint3 blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(x) alignas(x)
+
+namespace emul {
+
+constexpr int kMaxThreads = 1024;
+
+struct Warp {
+    pthread_barrier_t bar;
+    uint64_t slot[32];
+};
+struct Cta {
+    pthread_barrier_t bar;
+    int or_acc;
+    Warp warps[kMaxThreads / 32];
+    alignas(16) uint8_t dyn_smem[228 * 1024];
+};
+extern Cta g_cta;
+
+inline Warp &my_warp() { return g_cta.warps[threadIdx.x >> 5]; }
+inline unsigned my_lane() { return threadIdx.x & 31u; }
+
+template <class T>
+inline uint64_t to_bits(T v)
+{
+    static_assert(sizeof(T) <= 8, "warp collectives move at most 64 bits");
+    uint64_t b = 0;
+    memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <class T>
+inline T from_bits(uint64_t b)
+{
+    T v;
+    memcpy(&v, &b, sizeof(T));
+    return v;
+}
+
+// every lane deposits its value, reads what `pick` tells it to, and leaves only when everybody has read
+template <class T, class F>
+inline T exchange(T v, F pick)
+{
+    Warp &w = my_warp();
+    w.slot[my_lane()] = to_bits(v);
+    pthread_barrier_wait(&w.bar);
+    const T r = pick(w.slot);
+    pthread_barrier_wait(&w.bar);
+    return r;
+}
+
+// kernel launch: `fn` is the kernel body bound to its arguments
+void launch(dim3 grid, unsigned threads, void (*fn)(const void *), const void *args);
+
+}  // namespace emul
+
+#define EMUL_DYNAMIC_SMEM emul::g_cta.dyn_smem
+
+inline void __syncthreads() { pthread_barrier_wait(&emul::g_cta.bar); }
+inline int __syncthreads_or(int p)
+{
+    if (p) __atomic_store_n(&emul::g_cta.or_acc, 1, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&emul::g_cta.bar);
+    const int r = __atomic_load_n(&emul::g_cta.or_acc, __ATOMIC_SEQ_CST);
+    pthread_barrier_wait(&emul::g_cta.bar);
+    if (threadIdx.x == 0) emul::g_cta.or_acc = 0;
+    pthread_barrier_wait(&emul::g_cta.bar);
+    return r;
+}
+
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src)
+{
+    return emul::exchange(v, [&](const uint64_t *s) { return emul::from_bits<T>(s[src & 31]); });
+}
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, unsigned d)
+{
+    const unsigned l = emul::my_lane();
+    return emul::exchange(v, [&](const uint64_t *s) { return l >= d ? emul::from_bits<T>(s[l - d]) : v; });
+}
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, unsigned d)
+{
+    const unsigned l = emul::my_lane();
+    return emul::exchange(v, [&](const uint64_t *s) { return l + d < 32 ? emul::from_bits<T>(s[l + d]) : v; });
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int m)
+{
+    const unsigned l = emul::my_lane();
+    return emul::exchange(v, [&](const uint64_t *s) { return emul::from_bits<T>(s[(l ^ (unsigned)m) & 31]); });
+}
+inline unsigned __ballot_sync(unsigned, int pred)
+{
+    return emul::exchange<unsigned>(pred ? 1u : 0u, [&](const uint64_t *s) {
+        unsigned r = 0;
+        for (int i = 0; i < 32; ++i) r |= (s[i] ? 1u : 0u) << i;
+        return r;
+    });
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v)
+{
+    return emul::exchange<unsigned>(v, [&](const uint64_t *s) {
+        unsigned r = 0;
+        for (int i = 0; i < 32; ++i) r += (unsigned)s[i];
+        return r;
+    });
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v)
+{
+    return emul::exchange<unsigned>(v, [&](const uint64_t *s) {
+        unsigned r = 0;
+        for (int i = 0; i < 32; ++i) r = (unsigned)s[i] > r ? (unsigned)s[i] : r;
+        return r;
+    });
+}
+
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+inline unsigned __brev(unsigned x)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+    return r;
+}
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+// PRMT, default mode: selector nibble i picks byte (nibble & 7) of {x = bytes 0..3, y = bytes 4..7}; bit 3 of a
+// nibble replicates the sign of that byte
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
+{
+    const uint64_t pool = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned sel = (s >> (4 * i)) & 0xfu;
+        unsigned byte = (unsigned)(pool >> (8 * (sel & 7u))) & 0xffu;
+        if (sel & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)      // wrap mode
+{
+    sh &= 31u;
+    return (unsigned)(((((uint64_t)hi << 32) | lo) << sh) >> 32);
+}
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)
+{
+    sh &= 31u;
+    return (unsigned)((((uint64_t)hi << 32) | lo) >> sh);
+}
+inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned sh)     // clamp mode
+{
+    sh = sh > 32u ? 32u : sh;
+    return sh == 32u ? lo : __funnelshift_l(lo, hi, sh);
+}
+inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned sh)
+{
+    sh = sh > 32u ? 32u : sh;
+    return sh == 32u ? hi : __funnelshift_r(lo, hi, sh);
+}
+
+// hook of chunk_codec.cuh: which tiles stay at their published aggregate (see the kernel)
+bool mbc_emul_keep_aggregate(uint32_t tile);

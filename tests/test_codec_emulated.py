@@ -1,0 +1,149 @@
+"""The device serializer's kernel text (csrc/chunk_codec.cuh) executed on the CPU (tests/cuda_emul: one pthread
+per CUDA thread, CTAs in dispatch order) against the restated reference serializer, byte for byte.
+
+This is what checks the index arithmetic of rle_tiles -- look-back over several windows, records that straddle
+tiles, the aligned 16-byte word assembly and its ragged ends, the cut-off at n + 1 bytes -- in the container that
+has no GPU; `-m gpu` repeats the same shapes on the real device (tests/test_chunk_codec.py).  The emulator is
+test infrastructure, the product never builds it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL = os.path.join(HERE, "cuda_emul")
+CSRC = os.path.join(os.path.dirname(HERE), "distributedmandelbrot_b200", "csrc")
+SO = os.path.join(EMUL, "libcodec_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    srcs = [os.path.join(EMUL, "codec_emul.cpp"), os.path.join(EMUL, "cuda_emul.h"), os.path.join(CSRC, "chunk_codec.cuh")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(s) for s in srcs):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
+                               "-I", EMUL, "-I", CSRC, "-o", SO, srcs[0]], env=env)
+    lib = C.CDLL(SO)
+    lib.emul_serialize_chunks.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.emul_serialize_chunks.restype = C.c_int
+    return lib
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import chunk_codec
+    return chunk_codec
+
+
+def _aligned(nbytes, offset):
+    """uint8 view of nbytes whose address is `offset` past a 16-byte boundary."""
+    buf = np.zeros(nbytes + 48, np.uint8)
+    a = (-buf.ctypes.data) % 16 + offset
+    return buf[a:a + nbytes]
+
+
+def _serialize(emul, chunks, keep=1, in_off=0, out_off=0):
+    """chunks: list of equal-sized payloads -> list of (serialised bytes, info record)."""
+    n, nb = chunks[0].size, len(chunks)
+    pstride = (n + 15) // 16 * 16 + 16
+    src = _aligned(nb * pstride, in_off)
+    for k, p in enumerate(chunks):
+        src[k * pstride:k * pstride + n] = p
+    ostride = (n + 1 + 255) // 256 * 256
+    out = _aligned(nb * ostride, out_off)
+    out[:] = 0xEE
+    info = np.zeros(nb * 32, np.uint8)
+    assert emul.emul_serialize_chunks(src.ctypes.data, n, nb, pstride, out.ctypes.data, ostride, info.ctypes.data, keep) == 0
+    res = []
+    for k in range(nb):
+        rec = info[32 * k:32 * k + 32]
+        ln = int(rec[:8].view("<u8")[0])
+        o = out[k * ostride:(k + 1) * ostride]
+        assert (o[n + 1:] == 0xEE).all(), "wrote past n + 1 bytes"
+        res.append((o[:ln].tobytes(), rec.view("<u4")))
+    return res
+
+
+def _payload(rng, n, kind):
+    if kind == "runs":
+        p = np.repeat(rng.integers(0, 4, n // 3 + 2).astype(np.uint8), rng.integers(1, 12, n // 3 + 2))[:n]
+    elif kind == "noise":
+        p = rng.integers(0, 256, n).astype(np.uint8)
+    elif kind == "const":
+        p = np.full(n, 1, np.uint8)
+    elif kind == "long":
+        p = np.repeat(rng.integers(0, 256, n // 9000 + 2).astype(np.uint8), rng.integers(1, 30000, n // 9000 + 2))[:n]
+        if p.size < n:
+            p = np.concatenate([p, np.full(n - p.size, 9, np.uint8)])
+    elif kind == "dense_then_const":
+        p = np.concatenate([rng.integers(0, 256, n // 10).astype(np.uint8), np.full(n - n // 10, 3, np.uint8)])
+    elif kind == "const_then_noise":
+        p = np.concatenate([np.full(n // 2, 3, np.uint8), rng.integers(0, 256, n - n // 2).astype(np.uint8)])
+    elif kind == "seams":
+        p = (np.arange(n) // 8192 % 2).astype(np.uint8)                  # every run starts exactly on a tile boundary
+    elif kind == "pairs":
+        p = (np.arange(n) // 2 % 2).astype(np.uint8)                     # 2.5 output bytes per input byte, RLE impossible
+    else:
+        p = (np.arange(n) % 2).astype(np.uint8)
+    p = np.ascontiguousarray(p)
+    assert p.size == n
+    return p
+
+
+KINDS = ("runs", "noise", "const", "alt", "long", "dense_then_const", "const_then_noise", "seams", "pairs")
+
+
+def test_emulated_kernel_small_and_ragged(emul, codec):
+    rng = np.random.default_rng(5)
+    for n in [1, 2, 15, 16, 17, 31, 32, 33, 4095, 4097, 8191, 8192, 8193]:
+        for kind in KINDS:
+            p = _payload(rng, n, kind)
+            (blob, info), = _serialize(emul, [p])
+            want = codec.serialize(p)
+            assert blob == want, (n, kind)
+            assert info[3] == want[0] and info[4] == codec.entry_type(p)          # codec, IndexEntry.Type
+
+
+def test_emulated_kernel_many_tiles_and_lookback_modes(emul, codec):
+    """Several tiles: the look-back sums aggregates over more than one 32-tile window (keep = 2: no tile but the
+    first ever publishes an inclusive prefix), runs longer than 65535 bytes, records straddling tile seams."""
+    rng = np.random.default_rng(6)
+    for n, kinds, keeps in [(24577, KINDS, (0, 1)), (100_003, ("runs", "long", "const", "const_then_noise"), (1,)),
+                            (300_000, ("runs", "long"), (2,))]:
+        for kind in kinds:
+            p = _payload(rng, n, kind)
+            want = codec.serialize(p)
+            for keep in keeps:
+                (blob, _), = _serialize(emul, [p], keep=keep)
+                assert blob == want, (n, kind, keep)
+    # one run of 70 000 bytes (length needs 17 bits, it ends 8 tiles after it started), then short runs
+    p = np.concatenate([np.full(70_000, 7, np.uint8), _payload(rng, 12_345, "runs")])
+    (blob, _), = _serialize(emul, [p], keep=1)
+    assert blob == codec.serialize(p)
+
+
+def test_emulated_kernel_alignment_batches_and_threshold(emul, codec, oracle):
+    rng = np.random.default_rng(7)
+    # payload and output off 16-byte alignment: the byte-wise load path, every phase of the word assembly
+    p = _payload(rng, 20_001, "runs")
+    want = codec.serialize(p)
+    for in_off, out_off in [(0, 1), (0, 7), (0, 15), (3, 0), (5, 11)]:
+        (blob, _), = _serialize(emul, [p], in_off=in_off, out_off=out_off)
+        assert blob == want, (in_off, out_off)
+    # 5 * runs < n picks RLE, 5 * runs == n keeps Raw (DataChunk.cs:188)
+    for runs, n in [(20, 100), (19, 100), (21, 100), (819, 4096), (820, 4096), (3276, 16384), (3277, 16384)]:
+        lens = np.full(runs, n // runs)
+        lens[: n - lens.sum()] += 1
+        q = np.ascontiguousarray(np.repeat((np.arange(runs) % 251).astype(np.uint8), lens))
+        (blob, info), = _serialize(emul, [q])
+        assert blob == codec.serialize(q) and blob[0] == (1 if 5 * runs < n else 0), (runs, n)
+    # a batch (blockIdx.y = chunk) of real payloads: never / immediate / regular chunks at a small definition
+    d = 96
+    wl = [(8, 300, 0, 0), (8, 64, 3, 4), (4, 256, 1, 2), (16, 500, 5, 8)]
+    chunks = [oracle.process_workload(*w, d) for w in wl]
+    for (blob, info), payload, w in zip(_serialize(emul, chunks), chunks, wl):
+        want = codec.serialize(payload)
+        assert blob == want, w
+        assert int(info[4]) == codec.entry_type(payload)
