@@ -41,14 +41,17 @@ namespace mbc {
 
 constexpr int kThreads = 256;
 constexpr int kHalf = 16;                              // one 128-bit load
-constexpr int kBytesPerThread = 2 * kHalf;             // two loads in flight per thread
-constexpr int kTile = kThreads * kBytesPerThread;      // 8192 payload bytes per CTA
+constexpr int kBytesPerThread = 2 * kHalf;             // a thread's span: two loads, one 32-bit mask
+constexpr int kTile = kThreads * kBytesPerThread;      // 8192 payload bytes: one span per thread (also raw_fixup's CTA)
 constexpr int kWarps = kThreads / 32;
-// dynamic shared memory of rle_tiles: [15] the byte before the tile | [16, 16 + kTile) the tile |
-// uint16 list of the in-tile offsets of the run starts (+ the end-of-chunk sentinel on the last tile)
+// rle_tiles<S>: a CTA owns S consecutive 8 KiB pieces (a thread: span h at piece h, h = 0 .. S-1), i.e. a tile of
+// S * 8 KiB.  Dynamic shared memory: [15] the byte before the tile | [16, 16 + tile) the tile | uint16 list of the
+// in-tile offsets of the run starts (+ the end-of-chunk sentinel on the last tile)
+constexpr int kMaxSpans = 2;                           // the packed scan carries 16 bits per piece
 constexpr int kCopyOff = 16;
-constexpr int kListOff = kCopyOff + kTile;
-constexpr int kSmemBytes = kListOff + 2 * (kTile + 8);
+__host__ __device__ constexpr int tile_bytes(int spans) { return spans * kTile; }
+__host__ __device__ constexpr int list_off(int spans) { return kCopyOff + tile_bytes(spans); }
+__host__ __device__ constexpr int smem_bytes(int spans) { return list_off(spans) + 2 * (tile_bytes(spans) + 8); }
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -78,7 +81,7 @@ struct Batch {
     uint32_t *dead;               // dead[c] != 0: some tile of chunk c has seen 5 * runs >= n, RLE is ruled out (zeroed likewise)
     Meta *meta;                   // meta[c]
     size_t n;                     // payload bytes per chunk, < 2^32
-    uint32_t ntiles;              // 8 KiB tiles per chunk
+    uint32_t ntiles;              // tiles per chunk (of S * 8 KiB for rle_tiles<S>, of 8 KiB for raw_fixup)
     uint32_t n_chunks;
 };
 
@@ -155,13 +158,24 @@ __device__ __forceinline__ uint32_t span_mask_slow(const uint8_t *__restrict__ p
     return mask;
 }
 
+// status words travel through L2, device scope (every word is self-validating: no ordering between them is needed)
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
 {
+#ifdef MBC_EMULATE
     return *reinterpret_cast<const volatile unsigned long long *>(p);
+#else
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#endif
 }
 __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
 {
+#ifdef MBC_EMULATE
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
+#else
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" : : "l"(p), "l"(v) : "memory");
+#endif
 }
 
 // one look-back status: flag 0 while the two words are unpublished or belong to different publications
@@ -232,11 +246,14 @@ __device__ __forceinline__ uint32_t stream_byte(uint32_t s, uint32_t skip, uint3
     return f < 4u ? (len >> (8u * f)) & 0xffu : (uint32_t)cp[pos];    // runValue (DataChunkSerializer.cs:84,98)
 }
 
-// The single pass.  grid = tiles * n_chunks blocks in chunk-minor order (block id = tile * n_chunks + chunk): the
-// blocks in flight at any time belong to all chunks of the batch, so that as many look-back fronts advance side
-// by side.  kThreads threads, kSmemBytes of dynamic shared memory.
-__global__ void __launch_bounds__(kThreads, 6) rle_tiles(const Batch b)
+// The single pass.  grid = (n_chunks, tiles [, more tiles]): blockIdx.x = chunk runs fastest, so the blocks in
+// flight at any time belong to all chunks of the batch and as many look-back fronts advance side by side, while the
+// tiles of one chunk are still dispatched in increasing order.  kThreads threads, smem_bytes(S) of dynamic shared memory.
+template <int S>
+__global__ void __launch_bounds__(kThreads, S == 1 ? 6 : 4) rle_tiles(const Batch b)
 {
+    static_assert(S >= 1 && S <= kMaxSpans, "spans per thread");
+    constexpr uint32_t kTileS = (uint32_t)tile_bytes(S);
 #ifdef MBC_EMULATE
     uint8_t *smem = EMUL_DYNAMIC_SMEM;
 #else
@@ -246,32 +263,39 @@ __global__ void __launch_bounds__(kThreads, 6) rle_tiles(const Batch b)
     __shared__ uint32_t s_runs_before, s_last_before, s_ruled_out;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x / b.n_chunks, chunk = blockIdx.x - tile * b.n_chunks;
+    const uint32_t chunk = blockIdx.x, tile = blockIdx.z * gridDim.y + blockIdx.y;
+    if (tile >= b.ntiles) return;                                      // padding of a three-dimensional grid, behind every real tile
     const uint8_t *__restrict__ p = b.payloads + chunk * b.payload_stride;
     uint8_t *__restrict__ out = b.out + chunk * b.out_stride;
     TileStatus *status = b.status + (size_t)chunk * b.ntiles;
     const uint32_t n = (uint32_t)b.n;
-    const uint32_t tile_base = tile * (uint32_t)kTile;                 // < n
-    const uint32_t span = tid * (uint32_t)kBytesPerThread;             // in-tile offset of my 32 bytes
+    const uint32_t tile_base = tile * kTileS;                          // < n
+    const uint32_t span = tid * (uint32_t)kBytesPerThread;             // offset of my 32 bytes inside each 8 KiB piece
     const bool is_last_tile = tile + 1u == b.ntiles;
     // a tile is `regular` when all of it lies inside the payload and the payload is 16-byte aligned
-    const bool regular = (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && n - tile_base >= (uint32_t)kTile;
+    const bool regular = (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && n - tile_base >= kTileS;
 
-    // ---- 1. the tile, once: run-start mask of my span, the bytes themselves go to shared memory ----------
-    uint32_t mask;
-    {
+    // ---- 1. the tile, once: run-start masks of my spans, the bytes themselves go to shared memory ---------
+    uint32_t mask[S];
+#pragma unroll
+    for (int h = 0; h < S; ++h) {
         uint4 v0, v1;
         uint32_t prev;
-        const size_t base = (size_t)tile_base + span;
-        mask = regular ? span_mask_fast(p, base, v0, v1, prev) : span_mask_slow(p, base, n, v0, v1, prev);
-        *reinterpret_cast<uint4 *>(smem + kCopyOff + span) = v0;
-        *reinterpret_cast<uint4 *>(smem + kCopyOff + span + kHalf) = v1;
-        if (tid == 0) smem[kCopyOff - 1] = (uint8_t)prev;
+        const size_t base = (size_t)tile_base + (uint32_t)(h * kTile) + span;
+        mask[h] = regular ? span_mask_fast(p, base, v0, v1, prev) : span_mask_slow(p, base, n, v0, v1, prev);
+        *reinterpret_cast<uint4 *>(smem + kCopyOff + h * kTile + span) = v0;
+        *reinterpret_cast<uint4 *>(smem + kCopyOff + h * kTile + span + kHalf) = v1;
+        if (h == 0 && tid == 0) smem[kCopyOff - 1] = (uint8_t)prev;
     }
-    const uint32_t cnt = __popc(mask);
-    const uint32_t mylast = cnt ? span + 32u - (uint32_t)__clz(mask) : 0u;      // 1 + in-tile offset of my last start
+    // counts of the pieces packed 16 bits each (a piece holds at most 8192 starts), scanned together
+    uint32_t cnt = 0, mylast = 0;                                      // mylast: 1 + in-tile offset of my last start
+#pragma unroll
+    for (int h = 0; h < S; ++h) {
+        cnt |= (uint32_t)__popc(mask[h]) << (16 * h);
+        if (mask[h]) mylast = (uint32_t)(h * kTile) + span + 32u - (uint32_t)__clz(mask[h]);
+    }
 
-    // CTA-wide exclusive scan of the counts, total, and the last start of the tile
+    // CTA-wide exclusive scan of the counts, totals, and the last start of the tile
     uint32_t inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -292,10 +316,15 @@ __global__ void __launch_bounds__(kThreads, 6) rle_tiles(const Batch b)
         const uint32_t c = __shfl_up_sync(0xffffffffu, wsum, o);
         if (lane >= (uint32_t)o) wsum += c;
     }
-    const uint32_t tot = __shfl_sync(0xffffffffu, wsum, kWarps - 1);
-    const uint32_t wbase = __shfl_sync(0xffffffffu, wsum, warp) - w_cnt[warp];
+    const uint32_t tot_packed = __shfl_sync(0xffffffffu, wsum, kWarps - 1);
+    const uint32_t excl = __shfl_sync(0xffffffffu, wsum, warp) - w_cnt[warp] + inc - cnt;   // per piece: starts before my span
     const uint32_t totlast = __reduce_max_sync(0xffffffffu, lane < (uint32_t)kWarps ? w_last[lane] : 0u);
-    const uint32_t rank = wbase + inc - cnt;                           // starts of this tile before my span
+    uint32_t tot = 0, rank[S];                                         // rank[h]: starts of this tile before my span of piece h
+#pragma unroll
+    for (int h = 0; h < S; ++h) {
+        rank[h] = tot + ((excl >> (16 * h)) & 0xffffu);
+        tot += (tot_packed >> (16 * h)) & 0xffffu;
+    }
     const unsigned long long agg_last = totlast ? (unsigned long long)tile_base + totlast : 0ull;   // 1 + position in the chunk
 
     // ---- 2. publish the aggregate at once (tile 0: its inclusive prefix) ---------------------------------
@@ -309,29 +338,32 @@ __global__ void __launch_bounds__(kThreads, 6) rle_tiles(const Batch b)
     const bool emits = (tot != 0 && s_ruled_out == 0) || is_last_tile;
 
     // ---- 3. the list of run-start offsets (does not need the prefix: predecessors get time to publish) ----
-    uint16_t *s_pos = reinterpret_cast<uint16_t *>(smem + kListOff);
+    uint16_t *s_pos = reinterpret_cast<uint16_t *>(smem + list_off(S));
     if (emits) {
-        // filled from the top (the highest set bit is one FLO away), four entries per trip
-        uint16_t *q = s_pos + rank + cnt;
-        uint32_t m = mask;
+#pragma unroll
+        for (int h = 0; h < S; ++h) {
+            // filled from the top (the highest set bit is one FLO away), two entries per 32-bit store: halves the
+            // scattered shared-memory stores, which is what this kernel has the least of to spare
+            uint32_t e = rank[h] + (uint32_t)__popc(mask[h]);          // one past my top entry
+            const uint32_t off = (uint32_t)(h * kTile) + span, off2 = off * 0x10001u;
+            uint32_t m = mask[h];
+            if (m) {
+                if (e & 1u) {                                          // my top entry is the low half of a word whose high half is the next span's
+                    const uint32_t j = top_bit(m);
+                    s_pos[--e] = (uint16_t)(off + j);
+                    m ^= 1u << j;
+                }
+                uint32_t *qw = reinterpret_cast<uint32_t *>(s_pos + e);
 #pragma unroll 1
-        while (m) {                                                    // a short divergent loop: runs cluster
-            uint32_t j = top_bit(m);
-            q[-1] = (uint16_t)(span + j);
-            m ^= 1u << j;
-            if (!m) break;
-            j = top_bit(m);
-            q[-2] = (uint16_t)(span + j);
-            m ^= 1u << j;
-            if (!m) break;
-            j = top_bit(m);
-            q[-3] = (uint16_t)(span + j);
-            m ^= 1u << j;
-            if (!m) break;
-            j = top_bit(m);
-            q[-4] = (uint16_t)(span + j);
-            m ^= 1u << j;
-            q -= 4;
+                while (m & (m - 1u)) {                                 // a short divergent loop: runs cluster
+                    const uint32_t j1 = top_bit(m);
+                    m ^= 1u << j1;
+                    const uint32_t j0 = top_bit(m);
+                    m ^= 1u << j0;
+                    *--qw = off2 + ((j1 << 16) | j0);
+                }
+                if (m) reinterpret_cast<uint16_t *>(qw)[-1] = (uint16_t)(off + top_bit(m));   // my lowest entry, the high half of its word
+            }
         }
         // the end of the chunk closes its last run like one more start would
         if (is_last_tile && tid == 0) s_pos[tot] = (uint16_t)(n - tile_base);

@@ -1033,13 +1033,23 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.status = reinterpret_cast<mbc::TileStatus *>(static_cast<uint8_t *>(workspace_dev) + 256);
     b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
     b.n = n;
-    b.ntiles = (uint32_t)codec_tiles(n);
+    static const int spans = getenv("MB_CODEC_SPANS") ? atoi(getenv("MB_CODEC_SPANS")) : 2;               // DEV-ONLY A/B
+    const size_t tile = (size_t)mbc::tile_bytes(spans == 1 ? 1 : 2);
+    b.ntiles = (uint32_t)((n + tile - 1) / tile);
     b.n_chunks = n_chunks;
     b.dead = reinterpret_cast<uint32_t *>(b.status + (size_t)n_chunks * b.ntiles);
     // the look-back flags must start out invalid, the hints clear
     MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * (b.ntiles * sizeof(mbc::TileStatus) + sizeof(uint32_t)), st));
-    // chunk-minor block order: tiles * n_chunks <= 2^19 * 2^16 < 2^31 - 1 blocks
-    mbc::rle_tiles<<<b.ntiles * n_chunks, mbc::kThreads, mbc::kSmemBytes, st>>>(b);   // everything, for chunks that end up RLE
+    // blockIdx.x = chunk (fastest), tiles along y and, beyond 65535 of them, z
+    const uint32_t gy = b.ntiles < 65535u ? b.ntiles : 65535u, gz = (b.ntiles + gy - 1) / gy;
+    if (spans == 1) {
+        mbc::rle_tiles<1><<<dim3(n_chunks, gy, gz), mbc::kThreads, mbc::smem_bytes(1), st>>>(b);   // everything, for chunks that end up RLE
+    } else {
+        static const cudaError_t attr = cudaFuncSetAttribute(mbc::rle_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mbc::smem_bytes(2));
+        MB_CUDA(attr);
+        mbc::rle_tiles<2><<<dim3(n_chunks, gy, gz), mbc::kThreads, mbc::smem_bytes(2), st>>>(b);
+    }
+    b.ntiles = (uint32_t)codec_tiles(n);
     mbc::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc::kThreads, 0, st>>>(b);     // exits at once unless the chunk ended up Raw
     MB_CUDA(cudaGetLastError());
     return MB_OK;

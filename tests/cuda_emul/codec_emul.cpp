@@ -32,12 +32,13 @@ void *worker(void *arg)
     // the thread id was stored behind the job by launch()
     const unsigned t = *reinterpret_cast<const unsigned *>(reinterpret_cast<const char *>(arg) + sizeof(Job));
     threadIdx = emul_uint3{t, 0, 0};
-    for (unsigned by = 0; by < j->grid.y; ++by)
-        for (unsigned bx = 0; bx < j->grid.x; ++bx) {
-            blockIdx = emul_uint3{bx, by, 0};
-            j->fn(j->args);
-            pthread_barrier_wait(&emul::g_cta.bar);          // the next CTA reuses the shared memory
-        }
+    for (unsigned bz = 0; bz < j->grid.z; ++bz)
+        for (unsigned by = 0; by < j->grid.y; ++by)
+            for (unsigned bx = 0; bx < j->grid.x; ++bx) {    // dispatch order: x fastest
+                blockIdx = emul_uint3{bx, by, bz};
+                j->fn(j->args);
+                pthread_barrier_wait(&emul::g_cta.bar);      // the next CTA reuses the shared memory
+            }
     return nullptr;
 }
 }  // namespace
@@ -66,13 +67,15 @@ void emul::launch(dim3 grid, unsigned threads, void (*fn)(const void *), const v
     for (unsigned w = 0; w < threads / 32; ++w) pthread_barrier_destroy(&g_cta.warps[w].bar);
 }
 
-static void run_rle(const void *a) { mbc::rle_tiles(*static_cast<const mbc::Batch *>(a)); }
+static void run_rle1(const void *a) { mbc::rle_tiles<1>(*static_cast<const mbc::Batch *>(a)); }
+static void run_rle2(const void *a) { mbc::rle_tiles<2>(*static_cast<const mbc::Batch *>(a)); }
 static void run_raw(const void *a) { mbc::raw_fixup(*static_cast<const mbc::Batch *>(a)); }
 
 extern "C" int emul_serialize_chunks(const uint8_t *payloads, size_t n, uint32_t n_chunks, size_t payload_stride, uint8_t *out,
-                                     size_t out_stride, void *info, int keep_mode)
+                                     size_t out_stride, void *info, int keep_mode, int spans, unsigned grid_y)
 {
     if (!payloads || !out || !info || n == 0 || n >= 0xffffffffull || payload_stride < n || out_stride < n + 1) return 1;
+    if (spans < 1 || spans > mbc::kMaxSpans || grid_y == 0) return 1;
     g_keep_mode = keep_mode;
     mbc::Batch b;
     b.payloads = payloads;
@@ -81,13 +84,17 @@ extern "C" int emul_serialize_chunks(const uint8_t *payloads, size_t n, uint32_t
     b.out_stride = out_stride;
     b.meta = static_cast<mbc::Meta *>(info);
     b.n = n;
-    b.ntiles = (uint32_t)((n + mbc::kTile - 1) / mbc::kTile);
+    const size_t tile = (size_t)mbc::tile_bytes(spans);
+    b.ntiles = (uint32_t)((n + tile - 1) / tile);
     b.n_chunks = n_chunks;
     b.status = static_cast<mbc::TileStatus *>(calloc((size_t)n_chunks * b.ntiles + n_chunks, sizeof(mbc::TileStatus)));
     if (!b.status) return 2;
     b.dead = reinterpret_cast<uint32_t *>(b.status + (size_t)n_chunks * b.ntiles);
-    static_assert(mbc::kSmemBytes <= (int)sizeof(emul::g_cta.dyn_smem), "dynamic shared memory of the emulator");
-    emul::launch(dim3(b.ntiles * n_chunks, 1, 1), mbc::kThreads, run_rle, &b);
+    static_assert(mbc::smem_bytes(mbc::kMaxSpans) <= (int)sizeof(emul::g_cta.dyn_smem), "dynamic shared memory of the emulator");
+    // grid_y < tiles exercises the three-dimensional grid (and its padding blocks) of very large payloads
+    const unsigned gy = b.ntiles < grid_y ? b.ntiles : grid_y, gz = (b.ntiles + gy - 1) / gy;
+    emul::launch(dim3(n_chunks, gy, gz), mbc::kThreads, spans == 1 ? run_rle1 : run_rle2, &b);
+    b.ntiles = (uint32_t)((n + mbc::kTile - 1) / mbc::kTile);
     emul::launch(dim3(b.ntiles, n_chunks, 1), mbc::kThreads, run_raw, &b);
     free(b.status);
     return 0;

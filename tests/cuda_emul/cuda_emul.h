@@ -30,6 +30,7 @@ extern emul_uint3 blockDim, gridDim;
 
 #define __global__
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)

@@ -77,9 +77,10 @@ def test_device_serializer_golden_and_shapes(gpu, codec, golden_meta, golden_arr
         payload = np.ascontiguousarray(golden_arrays[rec["key"] + "_payload"])
         assert _serialize_gpu(gpu, payload) == golden_arrays[rec["key"] + "_serialized"].tobytes(), rec
     rng = np.random.default_rng(3)
-    # sizes around the 32-byte thread span and the 8 KiB tile of the single-pass kernel; run structures that
+    # sizes around the 32-byte thread span, the 8 KiB piece and the 16 KiB tile of the single-pass kernel; run structures that
     # straddle tiles (long runs), that make RLE impossible late / early, and that sit exactly on tile seams
-    for n in [1, 2, 15, 16, 17, 31, 32, 33, 4095, 4096, 4097, 8191, 8192, 8193, 16384, 16385, 24577, 100_003, 300_000, 1_000_000]:
+    for n in [1, 2, 15, 16, 17, 31, 32, 33, 4095, 4096, 4097, 8191, 8192, 8193, 16383, 16384, 16385, 24577, 32767, 32768, 32769, 100_003,
+              300_000, 1_000_000]:
         for kind in ("runs", "noise", "const", "alt", "long", "dense_then_const", "const_then_noise", "seams"):
             if kind == "runs":
                 p = np.repeat(rng.integers(0, 4, n // 3 + 2).astype(np.uint8), rng.integers(1, 12, n // 3 + 2))[:n]

@@ -26,7 +26,8 @@ def emul():
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
                                "-I", EMUL, "-I", CSRC, "-o", SO, srcs[0]], env=env)
     lib = C.CDLL(SO)
-    lib.emul_serialize_chunks.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.emul_serialize_chunks.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_uint]
     lib.emul_serialize_chunks.restype = C.c_int
     return lib
 
@@ -44,7 +45,7 @@ def _aligned(nbytes, offset):
     return buf[a:a + nbytes]
 
 
-def _serialize(emul, chunks, keep=1, in_off=0, out_off=0):
+def _serialize(emul, chunks, keep=1, in_off=0, out_off=0, spans=2, grid_y=65535):
     """chunks: list of equal-sized payloads -> list of (serialised bytes, info record)."""
     n, nb = chunks[0].size, len(chunks)
     pstride = (n + 15) // 16 * 16 + 16
@@ -55,7 +56,8 @@ def _serialize(emul, chunks, keep=1, in_off=0, out_off=0):
     out = _aligned(nb * ostride, out_off)
     out[:] = 0xEE
     info = np.zeros(nb * 32, np.uint8)
-    assert emul.emul_serialize_chunks(src.ctypes.data, n, nb, pstride, out.ctypes.data, ostride, info.ctypes.data, keep) == 0
+    assert emul.emul_serialize_chunks(src.ctypes.data, n, nb, pstride, out.ctypes.data, ostride, info.ctypes.data, keep,
+                                      spans, grid_y) == 0
     res = []
     for k in range(nb):
         rec = info[32 * k:32 * k + 32]
@@ -97,7 +99,7 @@ KINDS = ("runs", "noise", "const", "alt", "long", "dense_then_const", "const_the
 
 def test_emulated_kernel_small_and_ragged(emul, codec):
     rng = np.random.default_rng(5)
-    for n in [1, 2, 15, 16, 17, 31, 32, 33, 4095, 4097, 8191, 8192, 8193]:
+    for n in [1, 2, 15, 16, 17, 31, 32, 33, 4097, 8191, 8192, 8193, 16383, 16384, 16385]:
         for kind in KINDS:
             p = _payload(rng, n, kind)
             (blob, info), = _serialize(emul, [p])
@@ -106,12 +108,27 @@ def test_emulated_kernel_small_and_ragged(emul, codec):
             assert info[3] == want[0] and info[4] == codec.entry_type(p)          # codec, IndexEntry.Type
 
 
+def test_emulated_kernel_one_span_per_thread_and_3d_grid(emul, codec):
+    """rle_tiles<1> (8 KiB tiles) and a grid whose tile index is split over y and z, with padding blocks."""
+    rng = np.random.default_rng(8)
+    for n, kinds in [(8193, KINDS), (40_000, ("runs", "noise", "long", "const_then_noise"))]:
+        for kind in kinds:
+            p = _payload(rng, n, kind)
+            want = codec.serialize(p)
+            assert _serialize(emul, [p], spans=1)[0][0] == want, (n, kind)
+            assert _serialize(emul, [p], spans=2, grid_y=2)[0][0] == want, (n, kind)
+    chunks = [_payload(rng, 50_001, "runs"), _payload(rng, 50_001, "noise"), _payload(rng, 50_001, "long")]
+    for spans, gy in [(1, 3), (2, 3)]:
+        for (blob, _), p in zip(_serialize(emul, chunks, spans=spans, grid_y=gy), chunks):
+            assert blob == codec.serialize(p), (spans, gy)
+
+
 def test_emulated_kernel_many_tiles_and_lookback_modes(emul, codec):
     """Several tiles: the look-back sums aggregates over more than one 32-tile window (keep = 2: no tile but the
     first ever publishes an inclusive prefix), runs longer than 65535 bytes, records straddling tile seams."""
     rng = np.random.default_rng(6)
-    for n, kinds, keeps in [(24577, KINDS, (0, 1)), (100_003, ("runs", "long", "const", "const_then_noise"), (1,)),
-                            (300_000, ("runs", "long"), (2,))]:
+    for n, kinds, keeps in [(40_961, KINDS, (0, 1)), (100_003, ("runs", "long", "const", "const_then_noise"), (1,)),
+                            (600_000, ("runs", "long"), (2,))]:
         for kind in kinds:
             p = _payload(rng, n, kind)
             want = codec.serialize(p)
