@@ -51,7 +51,8 @@ constexpr int kMaxSpans = 2;                           // the packed scan carrie
 constexpr int kCopyOff = 16;
 __host__ __device__ constexpr int tile_bytes(int spans) { return spans * kTile; }
 __host__ __device__ constexpr int list_off(int spans) { return kCopyOff + tile_bytes(spans); }
-__host__ __device__ constexpr int smem_bytes(int spans) { return list_off(spans) + 2 * (tile_bytes(spans) + 8); }
+__host__ __device__ constexpr int list_cap(int) { return kTile; }           // entries the list holds (+ the sentinel): one piece's worst case
+__host__ __device__ constexpr int smem_bytes(int spans) { return list_off(spans) + 2 * (list_cap(spans) + 8); }
 
 // per-chunk result record (mb_chunk_info in include/mandelbrot_b200.h)
 struct Meta {
@@ -195,6 +196,7 @@ __device__ __forceinline__ void ld_pair(const TileStatus *st, uint32_t &flag, ui
 // done (the usual decoupled-look-back assumption).  One round trip to L2 inspects kLook * 32 predecessors: the
 // front of inclusive prefixes advances by that many tiles per round trip, which is what bounds a single chunk.
 constexpr int kLook = 4;
+constexpr uint32_t kRelay = 16;                                // idle tiles that publish an inclusive prefix: one in 16 (< 32 * kLook)
 __device__ __noinline__ unsigned long long look_back(const TileStatus *status, uint32_t tile, uint32_t lane)
 {
     uint32_t rb = 0, lb = 0;
@@ -250,7 +252,7 @@ __device__ __forceinline__ uint32_t stream_byte(uint32_t s, uint32_t skip, uint3
 // flight at any time belong to all chunks of the batch and as many look-back fronts advance side by side, while the
 // tiles of one chunk are still dispatched in increasing order.  kThreads threads, smem_bytes(S) of dynamic shared memory.
 template <int S>
-__global__ void __launch_bounds__(kThreads, S == 1 ? 6 : 4) rle_tiles(const Batch b)
+__global__ void __launch_bounds__(kThreads, S == 1 ? 8 : 6) rle_tiles(const Batch b)
 {
     static_assert(S >= 1 && S <= kMaxSpans, "spans per thread");
     constexpr uint32_t kTileS = (uint32_t)tile_bytes(S);
@@ -274,6 +276,12 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 6 : 4) rle_tiles(const Batc
     const bool is_last_tile = tile + 1u == b.ntiles;
     // a tile is `regular` when all of it lies inside the payload and the payload is 16-byte aligned
     const bool regular = (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && n - tile_base >= kTileS;
+
+    // RLE already ruled out by an earlier tile?  (a hint, read once per CTA so that all threads agree -- and first,
+    // so that its trip to L2 overlaps the tile's; a stale 0 only costs the work, and whoever set it saw
+    // 5 * runs >= n, so the chunk ends up Raw whatever is skipped)
+    uint32_t ruled_out_hint = 0;
+    if (tid == 0) ruled_out_hint = *reinterpret_cast<const volatile uint32_t *>(b.dead + chunk);
 
     // ---- 1. the tile, once: run-start masks of my spans, the bytes themselves go to shared memory ---------
     uint32_t mask[S];
@@ -305,9 +313,7 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 6 : 4) rle_tiles(const Batc
     const uint32_t wl = __reduce_max_sync(0xffffffffu, mylast);
     if (lane == 31) w_cnt[warp] = inc;
     if (lane == 0) w_last[warp] = wl;
-    // RLE already ruled out by an earlier tile?  (a hint, read once per CTA so that all threads agree; a stale 0
-    // only costs the work, and whoever set it saw 5 * runs >= n, so the chunk ends up Raw whatever is skipped)
-    if (tid == 0) s_ruled_out = *reinterpret_cast<const volatile uint32_t *>(b.dead + chunk);
+    if (tid == 0) s_ruled_out = ruled_out_hint;
     __syncthreads();
     // the eight warp totals are scanned by the first eight lanes of every warp
     uint32_t wsum = lane < (uint32_t)kWarps ? w_cnt[lane] : 0u;
@@ -334,137 +340,164 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 6 : 4) rle_tiles(const Batc
         st_status(&status[tile].last, flag | agg_last);
     }
     // a tile without a run start closes no run (unless it is the last one): it only passes the prefix on; so does
-    // a tile that found RLE ruled out
+    // a tile that found RLE ruled out.  Such a tile needs no prefix itself: its aggregate is published, and only
+    // every kRelay-th of them also looks back and publishes an inclusive prefix, which keeps everybody's look-back
+    // within one window without making every idle tile wait for a trip to L2.
     const bool emits = (tot != 0 && s_ruled_out == 0) || is_last_tile;
+    if (!emits && (tile & (kRelay - 1u)) != kRelay - 1u) return;      // uniform
 
-    // ---- 3. the list of run-start offsets (does not need the prefix: predecessors get time to publish) ----
+    // The list holds list_cap(S) = 8192 entries.  A tile of two pieces with more run starts than that (runs
+    // shorter than two bytes on average) is emitted piece by piece, in S rounds; every other tile in one.
     uint16_t *s_pos = reinterpret_cast<uint16_t *>(smem + list_off(S));
-    if (emits) {
-#pragma unroll
-        for (int h = 0; h < S; ++h) {
-            // filled from the top (the highest set bit is one FLO away), two entries per 32-bit store: halves the
-            // scattered shared-memory stores, which is what this kernel has the least of to spare
-            uint32_t e = rank[h] + (uint32_t)__popc(mask[h]);          // one past my top entry
-            const uint32_t off = (uint32_t)(h * kTile) + span, off2 = off * 0x10001u;
-            uint32_t m = mask[h];
-            if (m) {
-                if (e & 1u) {                                          // my top entry is the low half of a word whose high half is the next span's
-                    const uint32_t j = top_bit(m);
-                    s_pos[--e] = (uint16_t)(off + j);
-                    m ^= 1u << j;
-                }
-                uint32_t *qw = reinterpret_cast<uint32_t *>(s_pos + e);
-#pragma unroll 1
-                while (m & (m - 1u)) {                                 // a short divergent loop: runs cluster
-                    const uint32_t j1 = top_bit(m);
-                    m ^= 1u << j1;
-                    const uint32_t j0 = top_bit(m);
-                    m ^= 1u << j0;
-                    *--qw = off2 + ((j1 << 16) | j0);
-                }
-                if (m) reinterpret_cast<uint16_t *>(qw)[-1] = (uint16_t)(off + top_bit(m));   // my lowest entry, the high half of its word
-            }
-        }
-        // the end of the chunk closes its last run like one more start would
-        if (is_last_tile && tid == 0) s_pos[tot] = (uint16_t)(n - tile_base);
-    }
-
-    // ---- look-back by warp 0, inclusive prefix published for the successors ------------------------------
-    if (warp == 0) {
-        uint32_t rb = 0, lb = 0;
-        if (tile) {
-            const unsigned long long r = look_back(status, tile, lane);
-            rb = (uint32_t)r;
-            lb = (uint32_t)(r >> 32);
-            if (lane == 0) {
-#ifdef MBC_EMULATE
-                // the emulator runs the CTAs one after the other, so every predecessor would be inclusive:
-                // leave most tiles at their aggregate to exercise the summation over several windows
-                if (!mbc_emul_keep_aggregate(tile))
-#endif
-                {
-                    st_status(&status[tile].count, kFlagInclusive | ((unsigned long long)rb + tot));
-                    st_status(&status[tile].last, kFlagInclusive | (agg_last ? agg_last : (unsigned long long)lb));
-                }
-            }
-        }
-        if (lane == 0) { s_runs_before = rb; s_last_before = lb; }
-    }
-    if (!emits) return;                                                // uniform: nobody is left behind at the barrier
-    __syncthreads();
-    const uint32_t runs_before = s_runs_before, last_before = s_last_before;
-
-    // the last tile knows the run count: pick the codec, write header + length + classification
-    if (is_last_tile && tid == 0) {
-        Meta *meta = b.meta + chunk;
-        const uint32_t runs = runs_before + tot;
-        // DataChunk.cs:181-204: the first serializer (Raw) is kept unless RLE is strictly shorter
-        const bool rle = (unsigned long long)runs * 5ull < (unsigned long long)n;
-        meta->runs = runs;
-        meta->codec = rle ? 1u : 0u;
-        meta->out_len = 1ull + (rle ? (unsigned long long)runs * 5ull : (unsigned long long)n);
-        // one run of 0s = IsNeverChunk, one run of 1s = IsImmediateChunk (DataChunk.cs:82,87);
-        // Never is tested first (DataStorage.cs:74-77) but the two cannot both hold
-        const uint32_t first = p[0];
-        meta->first_value = first;
-        meta->entry_type = (runs == 1 && first == 0) ? 1u : (runs == 1 && first == 1) ? 2u : 0u;
-        out[0] = rle ? 0x01 : 0x00;        // Serializer.SerializeCode, DataChunkSerializer.cs:20-23
-    }
-
-    // ---- 4. records of the runs that END in this tile ----------------------------------------------------
-    // List entry e (e = 0 .. tot-1, plus the sentinel e = tot on the last tile) is the start with global index
-    // g = runs_before + e and closes run g - 1: length = this start minus the previous one, value = the byte
-    // before this start.  Record r lives at out[1 + 5r .. 1 + 5r + 5).  Once the runs before the tile make
-    // RLE impossible (5 * runs >= n keeps Raw, and runs only grow) nothing is emitted any more.
-    if ((unsigned long long)runs_before * 5ull >= (unsigned long long)n) {
-        if (tid == 0) *reinterpret_cast<volatile uint32_t *>(b.dead + chunk) = 1u;
-        return;
-    }
-    const uint32_t skip = runs_before ? 0u : 1u;                       // start 0 of the chunk closes nothing
-    const uint32_t first_rec = runs_before ? runs_before - 1u : 0u;    // first record this tile writes
-    const uint32_t n_ent = tot + (is_last_tile ? 1u : 0u);
-    const uint32_t n_rec = n_ent - skip;                               // tile 0 holds start 0, so n_ent >= skip
-    const unsigned long long out_lo = 1ull + 5ull * first_rec;         // <= n: the tile's record stream starts here
-    uint32_t slen = 5u * n_rec;                                        // ... and is this long;
-    if ((unsigned long long)slen > (unsigned long long)n + 1ull - out_lo)
-        slen = (uint32_t)((unsigned long long)n + 1ull - out_lo);      // bytes beyond n + 1 can never be part of an RLE result
-    uint8_t *dst = out + out_lo;
-    const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
-    const uint32_t before = last_before - 1u - tile_base;              // in-tile offset of the start before entry 0 (wraps below 0)
     const uint8_t *cp = smem + kCopyOff - 1;                           // cp[o] = the byte before in-tile offset o
-    // aligned words that lie completely inside the stream: word q covers stream bytes [16q - shift, 16q - shift + 16)
-    const uint32_t q_first = shift ? 1u : 0u, q_end = (shift + slen) >> 4;
-    for (uint32_t q = q_first + tid; q < q_end; q += kThreads) {
-        const uint32_t s0 = 16u * q - shift;
-        const uint32_t ra = s0 / 5u, phase = s0 - 5u * ra;             // first record of the word, and where the word starts in it
-        const uint32_t ea = ra + skip;
-        const uint16_t *e = s_pos + ea;
-        uint32_t pm = e[-1];                                           // (e = 0: the two bytes before the list, in bounds, unused)
-        if (ea == 0) pm = before;
-        const uint32_t p0 = e[0], p1 = e[1], p2 = e[2], p3 = e[3];     // a whole word always touches four records
-        const uint32_t l0 = p0 - pm, l1 = p1 - p0, l2 = p2 - p1, l3 = p3 - p2;
-        const uint32_t c0 = cp[p0], c1 = cp[p1], c2 = cp[p2], c3 = cp[p3];
-        // the 20 bytes of the four records: l0 | c0 l1[0..2] | l1[3] c1 l2[0..1] | l2[2..3] c2 l3[0] | l3[1..3] c3
-        const uint32_t w0 = l0;
-        const uint32_t w1 = __byte_perm(c0, l1, 0x6540);
-        const uint32_t w2 = __byte_perm(__byte_perm(l1, c1, 0x0043), l2, 0x5410);
-        const uint32_t w3 = __byte_perm(__byte_perm(l2, c2, 0x0432), l3, 0x4210);
-        const uint32_t w4 = __byte_perm(l3, c3, 0x4321);
-        const uint32_t sel = 0x3210u + 0x1111u * phase;                // bytes phase .. phase + 3 of a word pair
-        uint4 w;
-        w.x = __byte_perm(w0, w1, sel);
-        w.y = __byte_perm(w1, w2, sel);
-        w.z = __byte_perm(w2, w3, sel);
-        w.w = __byte_perm(w3, w4, sel);
-        *reinterpret_cast<uint4 *>(dst + s0) = w;
-    }
-    // the bytes before the first and after the last whole word (< 16 each; < 32 when there is no whole word)
-    if (warp == kWarps - 1) {
-        const bool any = q_end > q_first;
-        const uint32_t head_end = any ? 16u * q_first - shift : slen;
-        const uint32_t tail_lo = any ? 16u * q_end - shift : slen;
-        if (lane < head_end) dst[lane] = (uint8_t)stream_byte(lane, skip, before, s_pos, cp);
-        if (tail_lo + lane < slen) dst[tail_lo + lane] = (uint8_t)stream_byte(tail_lo + lane, skip, before, s_pos, cp);
+    const uint32_t n_rounds = (S > 1 && emits && tot > (uint32_t)list_cap(S)) ? (uint32_t)S : 1u;
+    uint32_t done = 0;                                                 // entries of the rounds before this one
+    uint32_t runs_before = 0, before = 0;
+#pragma unroll 1
+    for (uint32_t r = 0; r < n_rounds; ++r) {
+        const bool closes_chunk = is_last_tile && r + 1u == n_rounds;
+        uint32_t tot_r = tot;                                          // entries of this round
+        if (n_rounds > 1) tot_r = (tot_packed >> (16u * r)) & 0xffffu;
+
+        // ---- 3. the list of run-start offsets (does not need the prefix: predecessors get time to publish) ----
+        if (emits) {
+#pragma unroll
+            for (int h = 0; h < S; ++h) {
+                if (n_rounds > 1 && (uint32_t)h != r) continue;
+                // filled from the top (the highest set bit is one FLO away), two entries per 32-bit store: halves the
+                // scattered shared-memory stores, which is what this kernel has the least of to spare
+                uint32_t e = rank[h] - done + (uint32_t)__popc(mask[h]);   // one past my top entry
+                const uint32_t off = (uint32_t)(h * kTile) + span, off2 = off * 0x10001u;
+                uint32_t m = mask[h];
+                if (m) {
+                    if (e & 1u) {                                      // my top entry is the low half of a word whose high half is the next span's
+                        const uint32_t j = top_bit(m);
+                        s_pos[--e] = (uint16_t)(off + j);
+                        m ^= 1u << j;
+                    }
+                    uint32_t *qw = reinterpret_cast<uint32_t *>(s_pos + e);
+#pragma unroll 1
+                    while (m & (m - 1u)) {                             // a short divergent loop: runs cluster
+                        const uint32_t j1 = top_bit(m);
+                        m ^= 1u << j1;
+                        const uint32_t j0 = top_bit(m);
+                        m ^= 1u << j0;
+                        *--qw = off2 + ((j1 << 16) | j0);
+                    }
+                    if (m) reinterpret_cast<uint16_t *>(qw)[-1] = (uint16_t)(off + top_bit(m));   // my lowest entry, the high half of its word
+                }
+            }
+            // the end of the chunk closes its last run like one more start would
+            if (closes_chunk && tid == 0) s_pos[tot_r] = (uint16_t)(n - tile_base);
+        }
+
+        // ---- look-back by warp 0 (first round), inclusive prefix published for the successors ----------------
+        if (r == 0 && warp == 0) {
+            uint32_t rb = 0, lb = 0;
+            if (tile) {
+                const unsigned long long lr = look_back(status, tile, lane);
+                rb = (uint32_t)lr;
+                lb = (uint32_t)(lr >> 32);
+                if (lane == 0) {
+#ifdef MBC_EMULATE
+                    // the emulator runs the CTAs one after the other, so every predecessor would be inclusive:
+                    // leave most tiles at their aggregate to exercise the summation over several windows
+                    if (!mbc_emul_keep_aggregate(tile))
+#endif
+                    {
+                        st_status(&status[tile].count, kFlagInclusive | ((unsigned long long)rb + tot));
+                        st_status(&status[tile].last, kFlagInclusive | (agg_last ? agg_last : (unsigned long long)lb));
+                    }
+                }
+            }
+            if (lane == 0) { s_runs_before = rb; s_last_before = lb; }
+        }
+        if (!emits) return;                                            // uniform: nobody is left behind at the barrier
+        __syncthreads();
+        if (r == 0) {
+            runs_before = s_runs_before;
+            before = s_last_before - 1u - tile_base;                   // in-tile offset of the start before entry 0 (wraps below 0)
+            // the last tile knows the run count: pick the codec, write header + length + classification
+            if (is_last_tile && tid == 0) {
+                Meta *meta = b.meta + chunk;
+                const uint32_t runs = runs_before + tot;
+                // DataChunk.cs:181-204: the first serializer (Raw) is kept unless RLE is strictly shorter
+                const bool rle = (unsigned long long)runs * 5ull < (unsigned long long)n;
+                meta->runs = runs;
+                meta->codec = rle ? 1u : 0u;
+                meta->out_len = 1ull + (rle ? (unsigned long long)runs * 5ull : (unsigned long long)n);
+                // one run of 0s = IsNeverChunk, one run of 1s = IsImmediateChunk (DataChunk.cs:82,87);
+                // Never is tested first (DataStorage.cs:74-77) but the two cannot both hold
+                const uint32_t first = p[0];
+                meta->first_value = first;
+                meta->entry_type = (runs == 1 && first == 0) ? 1u : (runs == 1 && first == 1) ? 2u : 0u;
+                out[0] = rle ? 0x01 : 0x00;        // Serializer.SerializeCode, DataChunkSerializer.cs:20-23
+            }
+        } else {
+            before = s_last_before;                                    // left by the round before (in-tile offset already)
+        }
+
+        // ---- 4. records of the runs that END at this round's starts ------------------------------------------
+        // List entry e (e = 0 .. tot_r-1, plus the sentinel e = tot_r when the chunk ends here) is the start with
+        // global index g = runs_r + e and closes run g - 1: length = this start minus the previous one, value = the
+        // byte before this start.  Record k lives at out[1 + 5k .. 1 + 5k + 5).  Once the runs before make RLE
+        // impossible (5 * runs >= n keeps Raw, and runs only grow) nothing is emitted any more.
+        const uint32_t runs_r = runs_before + done;
+        if ((unsigned long long)runs_r * 5ull >= (unsigned long long)n) {
+            if (tid == 0) *reinterpret_cast<volatile uint32_t *>(b.dead + chunk) = 1u;
+            return;
+        }
+        const uint32_t skip = runs_r ? 0u : 1u;                        // start 0 of the chunk closes nothing
+        const uint32_t first_rec = runs_r ? runs_r - 1u : 0u;          // first record this round writes
+        const uint32_t n_ent = tot_r + (closes_chunk ? 1u : 0u);
+        const uint32_t n_rec = n_ent - skip;                           // tile 0 holds start 0, so n_ent >= skip there
+        const unsigned long long out_lo = 1ull + 5ull * first_rec;     // <= n: the round's record stream starts here
+        uint32_t slen = 5u * n_rec;                                    // ... and is this long;
+        if ((unsigned long long)slen > (unsigned long long)n + 1ull - out_lo)
+            slen = (uint32_t)((unsigned long long)n + 1ull - out_lo);  // bytes beyond n + 1 can never be part of an RLE result
+        uint8_t *dst = out + out_lo;
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+        // aligned words that lie completely inside the stream: word q covers stream bytes [16q - shift, 16q - shift + 16)
+        const uint32_t q_first = shift ? 1u : 0u, q_end = (shift + slen) >> 4;
+        for (uint32_t q = q_first + tid; q < q_end; q += kThreads) {
+            const uint32_t s0 = 16u * q - shift;
+            const uint32_t ra = s0 / 5u, phase = s0 - 5u * ra;         // first record of the word, and where the word starts in it
+            const uint32_t ea = ra + skip;
+            const uint16_t *e = s_pos + ea;
+            uint32_t pm = e[-1];                                       // (e = 0: the two bytes before the list, in bounds, unused)
+            if (ea == 0) pm = before;
+            const uint32_t p0 = e[0], p1 = e[1], p2 = e[2], p3 = e[3]; // a whole word always touches four records
+            const uint32_t l0 = p0 - pm, l1 = p1 - p0, l2 = p2 - p1, l3 = p3 - p2;
+            const uint32_t c0 = cp[p0], c1 = cp[p1], c2 = cp[p2], c3 = cp[p3];
+            // the 20 bytes of the four records: l0 | c0 l1[0..2] | l1[3] c1 l2[0..1] | l2[2..3] c2 l3[0] | l3[1..3] c3
+            const uint32_t w0 = l0;
+            const uint32_t w1 = __byte_perm(c0, l1, 0x6540);
+            const uint32_t w2 = __byte_perm(__byte_perm(l1, c1, 0x0043), l2, 0x5410);
+            const uint32_t w3 = __byte_perm(__byte_perm(l2, c2, 0x0432), l3, 0x4210);
+            const uint32_t w4 = __byte_perm(l3, c3, 0x4321);
+            const uint32_t sel = 0x3210u + 0x1111u * phase;            // bytes phase .. phase + 3 of a word pair
+            uint4 w;
+            w.x = __byte_perm(w0, w1, sel);
+            w.y = __byte_perm(w1, w2, sel);
+            w.z = __byte_perm(w2, w3, sel);
+            w.w = __byte_perm(w3, w4, sel);
+            *reinterpret_cast<uint4 *>(dst + s0) = w;
+        }
+        // the bytes before the first and after the last whole word (< 16 each; < 32 when there is no whole word)
+        if (warp == kWarps - 1) {
+            const bool any = q_end > q_first;
+            const uint32_t head_end = any ? 16u * q_first - shift : slen;
+            const uint32_t tail_lo = any ? 16u * q_end - shift : slen;
+            if (lane < head_end) dst[lane] = (uint8_t)stream_byte(lane, skip, before, s_pos, cp);
+            if (tail_lo + lane < slen) dst[tail_lo + lane] = (uint8_t)stream_byte(tail_lo + lane, skip, before, s_pos, cp);
+        }
+        if (r + 1u < n_rounds) {                                       // (never taken with one piece per tile)
+            // the next round overwrites the list: leave it the last start of this one (or what this round had)
+            __syncthreads();
+            if (tid == 0) s_last_before = tot_r ? (uint32_t)s_pos[tot_r - 1u] : before;
+            done += tot_r;
+            __syncthreads();
+        }
     }
 }
 

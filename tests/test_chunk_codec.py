@@ -106,6 +106,26 @@ def test_device_serializer_golden_and_shapes(gpu, codec, golden_meta, golden_arr
 
 
 @pytest.mark.gpu
+def test_device_serializer_tiles_denser_than_the_list(gpu, codec):
+    """Tiles with more run starts than the kernel's shared-memory list holds (emitted in two rounds) inside chunks
+    that still end up RLE; same payloads as tests/test_codec_emulated.py."""
+    rng = np.random.default_rng(9)
+    p = np.full(200_000, 3, np.uint8)
+    p[50_000:70_000] = rng.integers(0, 256, 20_000)
+    q = np.full(114_688, 5, np.uint8)
+    q[98_304:] = rng.integers(0, 256, 16_384)
+    a = np.full(180_224, 9, np.uint8)
+    a[32_768:49_152] = np.arange(16_384) % 2
+    a[65_536:81_920] = np.arange(16_384) // 2 % 2
+    big = np.full(16_777_216, 1, np.uint8)                       # a native-size chunk, one sixth of it noise
+    big[5_000_000:7_700_000] = rng.integers(0, 256, 2_700_000)
+    for x in (p, q, a, big):
+        want = codec.serialize(x)
+        assert want[0] == 1
+        assert _serialize_gpu(gpu, np.ascontiguousarray(x)) == want
+
+
+@pytest.mark.gpu
 def test_device_serializer_exactly_at_the_raw_rle_threshold(gpu, codec):
     # 5 * runs < n picks RLE, 5 * runs == n keeps Raw (DataChunk.cs:188)
     for runs, n in [(20, 100), (19, 100), (21, 100), (819, 4096), (820, 4096)]:

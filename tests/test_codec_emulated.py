@@ -141,6 +141,29 @@ def test_emulated_kernel_many_tiles_and_lookback_modes(emul, codec):
     assert blob == codec.serialize(p)
 
 
+def test_emulated_kernel_tiles_denser_than_the_list(emul, codec):
+    """A 16 KiB tile with more than 8192 run starts is emitted piece by piece (two rounds over one list); the
+    chunk as a whole still ends up RLE, so every byte of those rounds counts."""
+    rng = np.random.default_rng(9)
+    # noise island inside a constant chunk; it starts and ends inside tiles and covers whole tiles in between
+    p = np.full(200_000, 3, np.uint8)
+    p[50_000:70_000] = rng.integers(0, 256, 20_000)
+    # ... and a chunk whose LAST tile is the dense one (the end-of-chunk sentinel goes into the second round)
+    q = np.full(114_688, 5, np.uint8)
+    q[98_304:] = rng.integers(0, 256, 16_384)
+    # every byte a run start in one tile (both pieces hold exactly 8192 entries), alternating 2-byte runs elsewhere
+    a = np.full(180_224, 9, np.uint8)
+    a[32_768:49_152] = np.arange(16_384) % 2
+    a[65_536:81_920] = np.arange(16_384) // 2 % 2
+    for name, x in (("island", p), ("last", q), ("alt", a)):
+        want = codec.serialize(x)
+        assert want[0] == 1, name
+        for keep in (0, 1):
+            (blob, _), = _serialize(emul, [x], keep=keep)
+            assert blob == want, (name, keep)
+        assert _serialize(emul, [x], spans=1)[0][0] == want, name
+
+
 def test_emulated_kernel_alignment_batches_and_threshold(emul, codec, oracle):
     rng = np.random.default_rng(7)
     # payload and output off 16-byte alignment: the byte-wise load path, every phase of the word assembly
