@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libmandelbrot_b200.so")
 STAMP = SO + ".srchash"
 SOURCES = ["mandelbrot_capi.cu", "tile_wsq.cpp", "host_frame.cpp"]
-HEADERS = ["escape_kernels.cuh", "escape_refill.cuh", "chunk_codec.cuh", "chunk_codec_segments.cuh", os.path.join("..", "..", "include", "mandelbrot_b200.h")]
+HEADERS = ["escape_kernels.cuh", "escape_refill.cuh", "chunk_codec.cuh", os.path.join("..", "..", "include", "mandelbrot_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

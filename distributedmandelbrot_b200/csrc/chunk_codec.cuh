@@ -7,13 +7,14 @@
 //     byte 0 = codec: 0x00 raw -> the n payload bytes ; 0x01 RLE -> (uint32 LE runLength, uint8
 //     value) records, one per maximal run.  Raw wins ties (`<` with Raw first, DataChunk.cs:188).
 //
-// ONE pass over HBM for every chunk that ends up RLE (rle_tiles), one CTA per 8 KiB tile:
-//   1. the tile is loaded once (2 x 128-bit per thread), kept in shared memory, and its run starts are found
-//      with SWAR byte compares (one 32-bit mask per thread);
+// ONE pass over HBM for every chunk that ends up RLE (rle_tiles), one CTA per 16 KiB tile (two 8 KiB pieces):
+//   1. the tile is loaded once (4 x 128-bit per thread), kept in shared memory, and its run starts are found
+//      with SWAR byte compares (one 32-bit mask per 32-byte span);
 //   2. a decoupled look-back over the chunk's tiles carries (number of run starts, position of the last
 //      run start): a tile publishes its aggregate as soon as it has counted and sums its predecessors'
-//      aggregates back to the nearest published inclusive prefix;
-//   3. the in-tile offsets of the run starts are appended to a list in shared memory;
+//      aggregates back to the nearest published inclusive prefix, 128 predecessors per trip to L2; tiles that
+//      have nothing to emit only relay;
+//   3. the in-tile offsets of the run starts are appended to a list in shared memory, two per 32-bit store;
 //   4. records are emitted by the tile in which a run ENDS -- there both its length (this start minus the
 //      previous start, which the scan carries across tiles however long the run was) and its value (the
 //      byte before the new start) are known, so no second pass and no look-ahead are needed; the chunk's
@@ -21,9 +22,13 @@
 //      five list entries behind its four records, builds the 20-byte record stream in registers with byte
 //      permutes and stores the aligned 16 bytes it owns straight to global memory (no staging, no byte
 //      stores except at the two ragged ends of the tile's output range).
-// A tile stops emitting once the runs before it already make RLE impossible (5 * runs >= n).  Only a chunk
-// that ends up Raw takes a second kernel (raw_fixup), which copies the payload behind the header byte.
-// Traffic: n read + serialised bytes written for RLE chunks (the algorithmic minimum).
+// A tile stops emitting once the runs before it already make RLE impossible (5 * runs >= n), and later tiles of
+// that chunk are told so.  Only a chunk that ends up Raw takes a second kernel (raw_fixup), which copies the
+// payload behind the header byte.  Traffic: n read + serialised bytes written for RLE chunks (the algorithmic
+// minimum; measured 1.07 GB read / 0.95 GB written for 64 run-dense chunks of 16 MiB).
+// What bounds it (ncu, 64 run-dense chunks): instruction issue (76 % of the slots) and the shared-memory data
+// pipe (73 %) together, at 6 CTAs per SM; blocks run chunk-minor so that all chunks' look-back fronts advance
+// side by side.
 //
 // The file also compiles as plain C++ under tests/cuda_emul (MBC_EMULATE): a CPU execution of the very same
 // kernel text, one pthread per CUDA thread, which lets the index arithmetic be checked against the restated
@@ -503,7 +508,10 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 8 : 6) rle_tiles(const Batc
 
 // Second kernel, does work only for chunks that ended up Raw: RawSerializer
 // (DataChunkSerializer.cs:34-37), out[1 + i] = p[i].  The destination is 1 byte off alignment, so
-// aligned 16-byte words are built from two neighbouring source words.
+// aligned 16-byte words are built from two neighbouring source words.  grid = (pieces / kRawPieces, n_chunks):
+// a CTA owns kRawPieces consecutive 8 KiB pieces, so that the launch costs little when no chunk is Raw (the
+// usual case: a block that finds its chunk RLE exits at once, and there are few blocks).
+constexpr int kRawPieces = 4;
 __global__ void __launch_bounds__(kThreads) raw_fixup(const Batch b)
 {
     const Meta *__restrict__ meta = b.meta + blockIdx.y;
@@ -511,27 +519,30 @@ __global__ void __launch_bounds__(kThreads) raw_fixup(const Batch b)
     const uint8_t *__restrict__ p = b.payloads + blockIdx.y * b.payload_stride;
     uint8_t *__restrict__ out = b.out + blockIdx.y * b.out_stride;
     const size_t n = b.n;
+#pragma unroll 1
+    for (int piece = 0; piece < kRawPieces; ++piece) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        // 16-byte pieces, consecutive lanes on consecutive pieces (coalesced both ways)
-        const size_t base = (size_t)blockIdx.x * kTile + ((size_t)half * kThreads + threadIdx.x) * kHalf;
-        if (base >= n) return;
-        const bool fast = base + kHalf <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-        if (fast) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
-            const uint32_t before = base ? (uint32_t)p[base - 1] : 0u;             // header byte (0x00 = raw) for the very first word
-            uint4 w;
-            w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
-            w.y = __byte_perm(v.x, v.y, 0x6543);          // {v.x.b3, v.y.b0, v.y.b1, v.y.b2}
-            w.z = __byte_perm(v.y, v.z, 0x6543);
-            w.w = __byte_perm(v.z, v.w, 0x6543);
-            *reinterpret_cast<uint4 *>(out + base) = w;   // covers out[base .. base+15] = {p[base-1], p[base .. base+14]}
-            if (base + kHalf == n) out[n] = (uint8_t)(v.w >> 24);                  // last payload byte
-        } else {
-            // a word-building neighbour to the left leaves out[base] (= p[base-1]) to this thread
-            if (base) out[base] = p[base - 1];
-            for (int j = 0; j < kHalf && base + j < n; ++j) out[1 + base + j] = p[base + j];
+        for (int half = 0; half < 2; ++half) {
+            // 16-byte pieces, consecutive lanes on consecutive pieces (coalesced both ways)
+            const size_t base = ((size_t)blockIdx.x * kRawPieces + piece) * kTile + ((size_t)half * kThreads + threadIdx.x) * kHalf;
+            if (base >= n) return;
+            const bool fast = base + kHalf <= n && ((reinterpret_cast<uintptr_t>(p + base) & 15u) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+            if (fast) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(p + base);
+                const uint32_t before = base ? (uint32_t)p[base - 1] : 0u;         // header byte (0x00 = raw) for the very first word
+                uint4 w;
+                w.x = __byte_perm(before, v.x, 0x6540);       // {before.b0, v.x.b0, v.x.b1, v.x.b2}
+                w.y = __byte_perm(v.x, v.y, 0x6543);          // {v.x.b3, v.y.b0, v.y.b1, v.y.b2}
+                w.z = __byte_perm(v.y, v.z, 0x6543);
+                w.w = __byte_perm(v.z, v.w, 0x6543);
+                *reinterpret_cast<uint4 *>(out + base) = w;   // covers out[base .. base+15] = {p[base-1], p[base .. base+14]}
+                if (base + kHalf == n) out[n] = (uint8_t)(v.w >> 24);              // last payload byte
+            } else {
+                // a word-building neighbour to the left leaves out[base] (= p[base-1]) to this thread
+                if (base) out[base] = p[base - 1];
+                for (int j = 0; j < kHalf && base + j < n; ++j) out[1 + base + j] = p[base + j];
+            }
         }
     }
 }

@@ -18,7 +18,6 @@
 #include <vector>
 
 #include "chunk_codec.cuh"
-#include "chunk_codec_segments.cuh"   // DEV-ONLY A/B (MB_CODEC_SEGMENTS=1)
 #include "escape_kernels.cuh"
 #include "escape_refill.cuh"
 
@@ -1002,29 +1001,6 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     int rc = current_ctx(&c);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    static const bool use_segments = getenv("MB_CODEC_SEGMENTS") && atoi(getenv("MB_CODEC_SEGMENTS")) != 0;   // DEV-ONLY A/B
-    if (use_segments) {
-        mbc_seg::Batch b;
-        b.payloads = payloads_dev;
-        b.payload_stride = payload_stride;
-        b.out = out_dev;
-        b.out_stride = out_stride;
-        b.status = reinterpret_cast<mbc_seg::TileStatus *>(static_cast<uint8_t *>(workspace_dev) + 256);
-        b.meta = reinterpret_cast<mbc_seg::Meta *>(info_dev);
-        b.n = n;
-        b.ntiles = (uint32_t)codec_tiles(n);
-        const uint64_t want_ctas = (uint64_t)c->sm_count * 4;
-        uint64_t seg = ((uint64_t)b.ntiles * n_chunks + want_ctas - 1) / want_ctas;
-        if (seg < 1) seg = 1;
-        if (seg > 16) seg = 16;
-        b.seg_tiles = (uint32_t)seg;
-        b.nsegs = (b.ntiles + b.seg_tiles - 1) / b.seg_tiles;
-        MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * b.nsegs * sizeof(mbc_seg::TileStatus), st));
-        mbc_seg::rle_single_pass<<<dim3(b.nsegs, n_chunks, 1), mbc_seg::kThreads, mbc_seg::kStageBytes, st>>>(b);
-        mbc_seg::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc_seg::kThreads, 0, st>>>(b);
-        MB_CUDA(cudaGetLastError());
-        return MB_OK;
-    }
     mbc::Batch b;
     b.payloads = payloads_dev;
     b.payload_stride = payload_stride;
@@ -1033,8 +1009,8 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     b.status = reinterpret_cast<mbc::TileStatus *>(static_cast<uint8_t *>(workspace_dev) + 256);
     b.meta = reinterpret_cast<mbc::Meta *>(info_dev);
     b.n = n;
-    static const int spans = getenv("MB_CODEC_SPANS") ? atoi(getenv("MB_CODEC_SPANS")) : 2;               // DEV-ONLY A/B
-    const size_t tile = (size_t)mbc::tile_bytes(spans == 1 ? 1 : 2);
+    constexpr int kSpans = 2;                                      // 16 KiB tiles: measured best (profiles/r02_codec_bench.json)
+    const size_t tile = (size_t)mbc::tile_bytes(kSpans);
     b.ntiles = (uint32_t)((n + tile - 1) / tile);
     b.n_chunks = n_chunks;
     b.dead = reinterpret_cast<uint32_t *>(b.status + (size_t)n_chunks * b.ntiles);
@@ -1042,15 +1018,9 @@ int mb_serialize_chunks(const uint8_t *payloads_dev, size_t n, uint32_t n_chunks
     MB_CUDA(cudaMemsetAsync(b.status, 0, (size_t)n_chunks * (b.ntiles * sizeof(mbc::TileStatus) + sizeof(uint32_t)), st));
     // blockIdx.x = chunk (fastest), tiles along y and, beyond 65535 of them, z
     const uint32_t gy = b.ntiles < 65535u ? b.ntiles : 65535u, gz = (b.ntiles + gy - 1) / gy;
-    if (spans == 1) {
-        mbc::rle_tiles<1><<<dim3(n_chunks, gy, gz), mbc::kThreads, mbc::smem_bytes(1), st>>>(b);   // everything, for chunks that end up RLE
-    } else {
-        static const cudaError_t attr = cudaFuncSetAttribute(mbc::rle_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mbc::smem_bytes(2));
-        MB_CUDA(attr);
-        mbc::rle_tiles<2><<<dim3(n_chunks, gy, gz), mbc::kThreads, mbc::smem_bytes(2), st>>>(b);
-    }
+    mbc::rle_tiles<kSpans><<<dim3(n_chunks, gy, gz), mbc::kThreads, mbc::smem_bytes(kSpans), st>>>(b);   // everything, for chunks that end up RLE
     b.ntiles = (uint32_t)codec_tiles(n);
-    mbc::raw_fixup<<<dim3(b.ntiles, n_chunks, 1), mbc::kThreads, 0, st>>>(b);     // exits at once unless the chunk ended up Raw
+    mbc::raw_fixup<<<dim3((b.ntiles + mbc::kRawPieces - 1) / mbc::kRawPieces, n_chunks, 1), mbc::kThreads, 0, st>>>(b);   // exits at once unless the chunk ended up Raw
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -95,7 +95,7 @@ extern "C" int emul_serialize_chunks(const uint8_t *payloads, size_t n, uint32_t
     const unsigned gy = b.ntiles < grid_y ? b.ntiles : grid_y, gz = (b.ntiles + gy - 1) / gy;
     emul::launch(dim3(n_chunks, gy, gz), mbc::kThreads, spans == 1 ? run_rle1 : run_rle2, &b);
     b.ntiles = (uint32_t)((n + mbc::kTile - 1) / mbc::kTile);
-    emul::launch(dim3(b.ntiles, n_chunks, 1), mbc::kThreads, run_raw, &b);
+    emul::launch(dim3((b.ntiles + mbc::kRawPieces - 1) / mbc::kRawPieces, n_chunks, 1), mbc::kThreads, run_raw, &b);
     free(b.status);
     return 0;
 }
