@@ -31,7 +31,7 @@
 // side by side.
 //
 // The file also compiles as plain C++ under tests/cuda_emul (MBC_EMULATE): a CPU execution of the very same
-// kernel text, one pthread per CUDA thread, which lets the index arithmetic be checked against the restated
+// kernel text, one fiber per CUDA thread, which lets the index arithmetic be checked against the restated
 // serializer without a GPU (tests/test_codec_emulated.py).  The product never builds that way.
 #pragma once
 

@@ -1,21 +1,21 @@
-// cuda_emul.h -- TEST INFRASTRUCTURE: runs the text of a CUDA kernel on the CPU, one pthread per CUDA thread of a
-// CTA, CTAs one after the other in dispatch order (blockIdx.x fastest).  Just enough of the CUDA surface for
-// distributedmandelbrot_b200/csrc/chunk_codec.cuh: thread/block indices, __syncthreads, the warp shuffles / votes /
-// reductions the kernel uses, the integer intrinsics, uint4.  It exists so that the index arithmetic of the device
-// serializer can be checked against the restated reference serializer in a container without a GPU
-// (tests/test_codec_emulated.py).  Never part of the product build; nothing here is timed.
+// cuda_emul.h -- TEST INFRASTRUCTURE: runs the text of a CUDA kernel on the CPU.  Every CUDA thread of a CTA is a
+// fiber (its own stack, cooperative switching inside ONE OS thread); CTAs run one after the other in dispatch order
+// (blockIdx.x fastest).  Just enough of the CUDA surface for distributedmandelbrot_b200/csrc/chunk_codec.cuh:
+// thread/block indices, __syncthreads, the warp shuffles / votes / reductions the kernel uses, the integer
+// intrinsics, uint4.  It exists so that the index arithmetic of the device serializer can be checked against the
+// restated reference serializer in a container without a GPU (tests/test_codec_emulated.py).  Never part of the
+// product build; nothing here is timed.
 //
-// Semantics kept: all threads of a CTA run concurrently and meet at barriers; __shared__ variables are one per CTA
-// (CTAs are sequential, so a function-level static does it); warp collectives exchange through a per-warp slot array
-// between two warp barriers.  Not modelled: the memory model (everything is sequentially consistent enough through
-// the barriers), divergence inside a warp collective (the kernel never does that), more than one CTA in flight.
+// Semantics kept: the threads of a CTA make progress independently and meet at barriers (a fiber that waits at a
+// barrier yields to the next one); __shared__ variables are one per CTA (CTAs are sequential, so a function-level
+// static does it); warp collectives exchange through a per-warp slot array between two warp barriers.  Not
+// modelled: the memory model (a single OS thread is sequentially consistent), divergence inside a warp collective
+// (the kernel never does that), more than one CTA in flight (a look-back never has to wait: see the keep-aggregate
+// hook of the kernel for how its summation over several predecessors is still exercised).
 #pragma once
 
-#include <pthread.h>
 #include <stdint.h>
 #include <string.h>
-
-#include <vector>
 
 struct emul_uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -24,9 +24,6 @@ struct dim3 {
 };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
-
-extern thread_local emul_uint3 threadIdx, blockIdx;
-extern emul_uint3 blockDim, gridDim;
 
 #define __global__
 #define __device__
@@ -41,20 +38,43 @@ namespace emul {
 
 constexpr int kMaxThreads = 1024;
 
+struct Barrier {
+    unsigned count, arrived, generation;
+};
 struct Warp {
-    pthread_barrier_t bar;
+    Barrier bar;
     uint64_t slot[32];
 };
+struct Fiber {
+    void *sp;                     // saved stack pointer (x86-64) / context (elsewhere) while the fiber is not running
+    emul_uint3 tid, bid;
+    bool done;
+};
 struct Cta {
-    pthread_barrier_t bar;
+    Barrier bar;
     int or_acc;
     Warp warps[kMaxThreads / 32];
     alignas(16) uint8_t dyn_smem[228 * 1024];
 };
 extern Cta g_cta;
+extern Fiber *g_cur;              // the running fiber
+extern emul_uint3 g_block_dim, g_grid_dim;
 
-inline Warp &my_warp() { return g_cta.warps[threadIdx.x >> 5]; }
-inline unsigned my_lane() { return threadIdx.x & 31u; }
+void yield();                     // run the other fibers of the CTA once round, then come back
+
+inline void wait(Barrier &b)
+{
+    const unsigned g = b.generation;
+    if (++b.arrived == b.count) {
+        b.arrived = 0;
+        ++b.generation;
+    } else {
+        while (b.generation == g) yield();
+    }
+}
+
+inline Warp &my_warp() { return g_cta.warps[g_cur->tid.x >> 5]; }
+inline unsigned my_lane() { return g_cur->tid.x & 31u; }
 
 template <class T>
 inline uint64_t to_bits(T v)
@@ -78,9 +98,9 @@ inline T exchange(T v, F pick)
 {
     Warp &w = my_warp();
     w.slot[my_lane()] = to_bits(v);
-    pthread_barrier_wait(&w.bar);
+    wait(w.bar);
     const T r = pick(w.slot);
-    pthread_barrier_wait(&w.bar);
+    wait(w.bar);
     return r;
 }
 
@@ -89,17 +109,21 @@ void launch(dim3 grid, unsigned threads, void (*fn)(const void *), const void *a
 
 }  // namespace emul
 
+#define threadIdx (emul::g_cur->tid)
+#define blockIdx (emul::g_cur->bid)
+#define blockDim (emul::g_block_dim)
+#define gridDim (emul::g_grid_dim)
 #define EMUL_DYNAMIC_SMEM emul::g_cta.dyn_smem
 
-inline void __syncthreads() { pthread_barrier_wait(&emul::g_cta.bar); }
+inline void __syncthreads() { emul::wait(emul::g_cta.bar); }
 inline int __syncthreads_or(int p)
 {
-    if (p) __atomic_store_n(&emul::g_cta.or_acc, 1, __ATOMIC_SEQ_CST);
-    pthread_barrier_wait(&emul::g_cta.bar);
-    const int r = __atomic_load_n(&emul::g_cta.or_acc, __ATOMIC_SEQ_CST);
-    pthread_barrier_wait(&emul::g_cta.bar);
+    if (p) emul::g_cta.or_acc = 1;
+    emul::wait(emul::g_cta.bar);
+    const int r = emul::g_cta.or_acc;
+    emul::wait(emul::g_cta.bar);
     if (threadIdx.x == 0) emul::g_cta.or_acc = 0;
-    pthread_barrier_wait(&emul::g_cta.bar);
+    emul::wait(emul::g_cta.bar);
     return r;
 }
 

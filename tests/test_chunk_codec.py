@@ -125,6 +125,82 @@ def test_device_serializer_tiles_denser_than_the_list(gpu, codec):
         assert _serialize_gpu(gpu, np.ascontiguousarray(x)) == want
 
 
+def _serialize_device_batch(native, chunks, payload_stride=None):
+    """mb_serialize_chunks on device buffers (the batched C-ABI entry): list of equal-sized numpy payloads ->
+    list of (bytes, info record); the payloads sit payload_stride apart (default: back to back)."""
+    import torch
+    lib = native.lib()
+    n, nb = chunks[0].size, len(chunks)
+    ps = payload_stride or n
+    stride = lib.mb_serialize_out_stride(n)
+    wsb = lib.mb_serialize_workspace_bytes(n, nb)
+    src = torch.zeros(nb * ps, dtype=torch.uint8, device="cuda")
+    for k, c in enumerate(chunks):
+        src[k * ps:k * ps + n] = torch.from_numpy(c).cuda()
+    out = torch.full((nb * stride,), 0xEE, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    info = torch.zeros(nb * 32, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    native.check(lib.mb_serialize_chunks(src.data_ptr(), n, nb, ps, out.data_ptr(), stride, ws.data_ptr(), wsb, info.data_ptr(), st))
+    torch.cuda.synchronize()
+    recs = info.cpu().numpy()
+    res = []
+    for k in range(nb):
+        ln = int(recs[32 * k:32 * k + 8].view("<u8")[0])
+        o = out[k * stride:(k + 1) * stride]
+        assert bool((o[n + 1:] == 0xEE).all()), "wrote past n + 1 bytes"
+        res.append((o[:ln].cpu().numpy().tobytes(), recs[32 * k:32 * k + 32].view("<u4")))
+    return res
+
+
+@pytest.mark.gpu
+def test_device_serializer_unaligned_chunks_of_a_batch(gpu, codec):
+    """n not a multiple of 16 with the payloads back to back: every chunk but the first starts off 16-byte alignment
+    (the byte-wise load path on the device), and the second batch entry point argument, payload_stride > n."""
+    rng = np.random.default_rng(11)
+    n = 40_003
+    chunks = [np.ascontiguousarray(np.repeat(rng.integers(0, 5, n // 4 + 2).astype(np.uint8), rng.integers(1, 9, n // 4 + 2))[:n]) for _ in range(5)]
+    chunks[2] = rng.integers(0, 256, n).astype(np.uint8)                      # one Raw chunk among them
+    for ps in (None, n + 13, n + 29):
+        for (blob, info), c in zip(_serialize_device_batch(gpu, chunks, ps), chunks):
+            assert blob == codec.serialize(c), ps
+            assert int(info[2]) == 1 + int(np.count_nonzero(c[1:] != c[:-1]))
+
+
+@pytest.mark.gpu
+def test_device_serializer_more_than_65535_tiles(gpu, codec):
+    """1 GiB + 5 bytes = 65 537 tiles of 16 KiB: the tile index is split over two grid dimensions (with padding
+    blocks behind the last tile), positions and run lengths need 31 bits.  The expected bytes are written down by
+    hand (a 1 GiB payload is not put through the numpy restatement)."""
+    import struct
+    import torch
+    lib = gpu.lib()
+    n = 65_536 * 16_384 + 5
+    marks = [(0, 9), (16_383, 8), (700_000_001, 7), (n - 1, 6)]               # single bytes that differ from the background 5
+    src = torch.full((n,), 5, dtype=torch.uint8, device="cuda")
+    for pos, v in marks:
+        src[pos] = v
+    want, at = b"\x01", 0
+    for pos, v in marks:
+        if pos > at:
+            want += struct.pack("<IB", pos - at, 5)
+        want += struct.pack("<IB", 1, v)
+        at = pos + 1
+    assert at == n
+    stride = lib.mb_serialize_out_stride(n)
+    wsb = lib.mb_serialize_workspace_bytes(n, 1)
+    out = torch.full((stride,), 0xEE, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    info = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    gpu.check(lib.mb_serialize_chunks(src.data_ptr(), n, 1, n, out.data_ptr(), stride, ws.data_ptr(), wsb, info.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    rec = info.cpu().numpy()
+    assert int(rec[:8].view("<u8")[0]) == len(want) and int(rec[8:12].view("<u4")[0]) == (len(want) - 1) // 5
+    assert out[:len(want)].cpu().numpy().tobytes() == want
+    assert bool((out[len(want):len(want) + 4096] == 0xEE).all())
+
+
 @pytest.mark.gpu
 def test_device_serializer_exactly_at_the_raw_rle_threshold(gpu, codec):
     # 5 * runs < n picks RLE, 5 * runs == n keeps Raw (DataChunk.cs:188)

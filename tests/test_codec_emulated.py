@@ -1,5 +1,5 @@
-"""The device serializer's kernel text (csrc/chunk_codec.cuh) executed on the CPU (tests/cuda_emul: one pthread
-per CUDA thread, CTAs in dispatch order) against the restated reference serializer, byte for byte.
+"""The device serializer's kernel text (csrc/chunk_codec.cuh) executed on the CPU (tests/cuda_emul: one fiber per
+CUDA thread, CTAs in dispatch order) against the restated reference serializer, byte for byte.
 
 This is what checks the index arithmetic of rle_tiles -- look-back over several windows, records that straddle
 tiles, the aligned 16-byte word assembly and its ragged ends, the cut-off at n + 1 bytes -- in the container that
@@ -23,7 +23,7 @@ def emul():
     srcs = [os.path.join(EMUL, "codec_emul.cpp"), os.path.join(EMUL, "cuda_emul.h"), os.path.join(CSRC, "chunk_codec.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(s) for s in srcs):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
                                "-I", EMUL, "-I", CSRC, "-o", SO, srcs[0]], env=env)
     lib = C.CDLL(SO)
     lib.emul_serialize_chunks.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
@@ -108,6 +108,34 @@ def test_emulated_kernel_small_and_ragged(emul, codec):
             want = codec.serialize(p)
             assert blob == want, (n, kind)
             assert info[3] == want[0] and info[4] == codec.entry_type(p)          # codec, IndexEntry.Type
+
+
+def test_emulated_kernel_golden_fixtures_and_the_gpu_suite_shapes(emul, codec, golden_meta, golden_arrays):
+    """The serialised fixtures the reference viewer's decoder accepted (oracle/gen_golden.py), and the same sizes x
+    run structures the device suite runs (tests/test_chunk_codec.py), through both tile geometries."""
+    for rec in golden_meta["codec"]:
+        payload = np.ascontiguousarray(golden_arrays[rec["key"] + "_payload"])
+        assert _serialize(emul, [payload])[0][0] == golden_arrays[rec["key"] + "_serialized"].tobytes(), rec
+    rng = np.random.default_rng(3)
+    for n in [4095, 4096, 24_577, 32_767, 32_768, 32_769, 100_003, 300_000, 1_000_000]:
+        for kind in KINDS:
+            p = _payload(rng, n, kind)
+            want = codec.serialize(p)
+            assert _serialize(emul, [p], keep=1)[0][0] == want, (n, kind)
+            assert _serialize(emul, [p], keep=0, spans=1)[0][0] == want, (n, kind)
+
+
+def test_emulated_kernel_native_chunks(emul, codec, oracle):
+    """Whole 4096 x 4096 DataChunks as the worker renders them (16 MiB, 1024 tiles): a regular chunk, a Never and an
+    Immediate one, serialised as one batch; the regular one again with every inclusive prefix withheld."""
+    wl = [(4, 256, 1, 2), (8, 64, 3, 4), (8, 300, 0, 0)]
+    chunks = [oracle.process_workload(*w, 4096) for w in wl]
+    want = [codec.serialize(c) for c in chunks]
+    for (blob, info), c, w, ws in zip(_serialize(emul, chunks, keep=1), chunks, want, wl):
+        assert blob == w, ws
+        assert int(info[4]) == codec.entry_type(c) and int(info[3]) == w[0]
+    assert [codec.entry_type(c) for c in chunks] == [0, 1, 2]
+    assert _serialize(emul, [chunks[0]], keep=2)[0][0] == want[0]
 
 
 def test_emulated_kernel_one_span_per_thread_and_3d_grid(emul, codec):
