@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 8 : 6) rle_tiles(const Batc
 // aligned 16-byte words are built from two neighbouring source words.  grid = (pieces / kRawPieces, n_chunks):
 // a CTA owns kRawPieces consecutive 8 KiB pieces, so that the launch costs little when no chunk is Raw (the
 // usual case: a block that finds its chunk RLE exits at once, and there are few blocks).
-constexpr int kRawPieces = 4;
+constexpr int kRawPieces = 8;
 __global__ void __launch_bounds__(kThreads) raw_fixup(const Batch b)
 {
     const Meta *__restrict__ meta = b.meta + blockIdx.y;
