@@ -77,7 +77,7 @@ struct TileStatus {
 };
 constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagInclusive = 2ull << 62, kFlagMask = 3ull << 62;
 
-// A batch of chunks is processed by one set of launches: blockIdx.y = chunk.
+// A batch of chunks is processed by one set of launches (rle_tiles: blockIdx.x = chunk, raw_fixup: blockIdx.y).
 struct Batch {
     const uint8_t *payloads;      // chunk c at payloads + c * payload_stride
     size_t payload_stride;
