@@ -162,6 +162,48 @@ def cpu_baseline(spec, budget_s: float = 15.0):
                       f"{threads} pthreads, one dynamic (chunk,row) queue; cgroup cpu quota: {cpu_quota()}"}, d
 
 
+def serializer_row(nat, torch, nb: int = 64, iters: int = 5) -> dict:
+    """Informational row for the other hand-written kernel on the worker's path: the device
+    DataChunk serializer on `nb` copies of the run-dense boundary chunk of the cfg4 frame, one set of launches,
+    payloads resident in HBM, L2 flushed before every call, CUDA events on the launching stream.  Algorithmic bytes =
+    payload read once + serialised bytes written; peak = MEASURED_PEAKS.json's copy bandwidth.  Same measurement as
+    scripts/bench_codec.py (profiles/r02_codec_bench.json).  Not part of `value`, `e2e` or `roofline`."""
+    L = nat.lib()
+    n = 4096 * 4096
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    st = torch.cuda.current_stream().cuda_stream
+    one = torch.empty(n, dtype=torch.uint8, device="cuda")
+    t = nat.chunk_geometry(800, 250, 420, 4096, 10000)
+    nat.check(L.mb_render_u8(ctypes.byref(t), 1, one.data_ptr(), 0, st))
+    payload = one.repeat(nb)
+    stride = L.mb_serialize_out_stride(n)
+    ws_bytes = L.mb_serialize_workspace_bytes(n, nb)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    out = torch.empty(nb * stride, dtype=torch.uint8, device="cuda")
+    info = torch.empty(nb * 32, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    times = []
+    for _ in range(iters):
+        flush.fill_(1)                                   # evict the payloads from the 126 MB L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nat.check(L.mb_serialize_chunks(payload.data_ptr(), n, nb, n, out.data_ptr(), stride, ws.data_ptr(), ws_bytes, info.data_ptr(), st))
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    rec = info[:32].cpu().numpy()
+    olen, runs = int(rec[:8].view("<u8")[0]), int(rec[8:12].view("<u4")[0])
+    gbs = nb * (n + olen) / (ms * 1e-3) / 1e9
+    return {"kernel": "mbc::rle_tiles<2> (+ status memset, raw_fixup)", "workload": "64 x DataChunk (800, 250, 420) mrd=10000, 16 MiB each",
+            "chunks_per_call": nb, "runs_per_chunk": runs, "serialized_bytes_per_chunk": olen, "ms_median": ms, "us_per_chunk": ms * 1e3 / nb,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+            "l2": "256 MiB written between calls", "iters": iters}
+
+
 def run_reference(args, spec):
     """Reference arm: the CPU implementation of the path (the oracle port) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -210,6 +252,7 @@ def main() -> None:
                          "into rank 0's frame buffer over NVLink peer memory (no gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shortcut", action="store_true", help="skip the separately reported periodicity-shortcut legs")
+    ap.add_argument("--no-serializer-row", action="store_true", help="skip the informational device-serializer row (N = 1)")
     ap.add_argument("--refill", type=int, default=None, choices=[0, 1],
                     help="1 = persistent-warp kernel with lane refill (MB_TILE_LANE_REFILL), 0 = one warp per 8x4 patch; "
                          "default: the workload's own setting (frame.CONFIGS)")
@@ -500,6 +543,11 @@ def main() -> None:
                                              "unchanged, executed work reduced; never used for `value` or `roofline`"}
         if e2e_sc is not None:
             out["e2e_shortcut"] = e2e_sc
+        if not args.no_serializer_row and world == 1:
+            try:
+                out["serializer"] = serializer_row(nat, torch)
+            except Exception as exc:  # noqa: BLE001 -- informational row only, never fails the bench
+                out["serializer"] = {"error": repr(exc)}
         if not args.no_cpu_baseline and world == 1:      # timed on rank 0 at N = 1 only
             out["cpu_baseline"], d_used = cpu_baseline(spec)
             try:
