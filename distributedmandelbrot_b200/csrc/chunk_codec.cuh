@@ -30,12 +30,12 @@
 // pipe (73 %) together, at 6 CTAs per SM; blocks run chunk-minor so that all chunks' look-back fronts advance
 // side by side.
 //
-// The file also compiles as plain C++ under tests/cuda_emul (MBC_EMULATE): a CPU execution of the very same
+// The file also compiles as plain C++ under tests/cuda_emul (MB_EMULATE): a CPU execution of the very same
 // kernel text, one fiber per CUDA thread, which lets the index arithmetic be checked against the restated
 // serializer without a GPU (tests/test_codec_emulated.py).  The product never builds that way.
 #pragma once
 
-#ifdef MBC_EMULATE
+#ifdef MB_EMULATE
 #include "cuda_emul.h"
 #else
 #include <cuda_runtime.h>
@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t push4(uint32_t mask, uint32_t h)
 // index of the highest set bit of m != 0 (one FLO)
 __device__ __forceinline__ uint32_t top_bit(uint32_t m)
 {
-#ifdef MBC_EMULATE
+#ifdef MB_EMULATE
     return 31u - (uint32_t)__clz(m);
 #else
     uint32_t r;
@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t span_mask_slow(const uint8_t *__restrict__ p
 // status words travel through L2, device scope (every word is self-validating: no ordering between them is needed)
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
 {
-#ifdef MBC_EMULATE
+#ifdef MB_EMULATE
     return *reinterpret_cast<const volatile unsigned long long *>(p);
 #else
     unsigned long long v;
@@ -177,7 +177,7 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 }
 __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
 {
-#ifdef MBC_EMULATE
+#ifdef MB_EMULATE
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
 #else
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" : : "l"(p), "l"(v) : "memory");
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 8 : 6) rle_tiles(const Batc
 {
     static_assert(S >= 1 && S <= kMaxSpans, "spans per thread");
     constexpr uint32_t kTileS = (uint32_t)tile_bytes(S);
-#ifdef MBC_EMULATE
+#ifdef MB_EMULATE
     uint8_t *smem = EMUL_DYNAMIC_SMEM;
 #else
     extern __shared__ __align__(16) uint8_t smem[];
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, S == 1 ? 8 : 6) rle_tiles(const Batc
                 rb = (uint32_t)lr;
                 lb = (uint32_t)(lr >> 32);
                 if (lane == 0) {
-#ifdef MBC_EMULATE
+#ifdef MB_EMULATE
                     // the emulator runs the CTAs one after the other, so every predecessor would be inclusive:
                     // leave most tiles at their aggregate to exercise the summation over several windows
                     if (!mbc_emul_keep_aggregate(tile))

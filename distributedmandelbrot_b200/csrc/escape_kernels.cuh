@@ -23,7 +23,11 @@
 // escape), which issues on the ALU pipe in the FP64 pipe's shadow.
 #pragma once
 
+#ifdef MB_EMULATE            // tests/cuda_emul: the same kernel text executed on the CPU (test infrastructure, never the product)
+#include "cuda_emul.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/mandelbrot_b200.h"

@@ -1,10 +1,13 @@
 // cuda_emul.h -- TEST INFRASTRUCTURE: runs the text of a CUDA kernel on the CPU.  Every CUDA thread of a CTA is a
 // fiber (its own stack, cooperative switching inside ONE OS thread); CTAs run one after the other in dispatch order
-// (blockIdx.x fastest).  Just enough of the CUDA surface for distributedmandelbrot_b200/csrc/chunk_codec.cuh:
-// thread/block indices, __syncthreads, the warp shuffles / votes / reductions the kernel uses, the integer
-// intrinsics, uint4.  It exists so that the index arithmetic of the device serializer can be checked against the
-// restated reference serializer in a container without a GPU (tests/test_codec_emulated.py).  Never part of the
-// product build; nothing here is timed.
+// (blockIdx.x fastest).  Just enough of the CUDA surface for the kernels under distributedmandelbrot_b200/csrc/
+// (escape_kernels.cuh, escape_refill.cuh, chunk_codec.cuh): thread/block indices, __syncthreads, the warp shuffles /
+// votes / reductions they use, atomicAdd, the integer intrinsics, the *_rn floating-point intrinsics (plain IEEE
+// operations: this code is compiled with -ffp-contract=off, fma() is the correctly rounded one), small vector types.
+// It exists so that the kernels' logic -- the deferred escape test with its replay, the lane refill, the
+// serializer's index arithmetic -- can be checked against the CPU oracle / the restated reference serializer in a
+// container without a GPU (tests/test_escape_emulated.py, tests/test_codec_emulated.py).  Never part of the product
+// build; nothing here is timed.
 //
 // Semantics kept: the threads of a CTA make progress independently and meet at barriers (a fiber that waits at a
 // barrier yields to the next one); __shared__ variables are one per CTA (CTAs are sequential, so a function-level
@@ -14,6 +17,7 @@
 // hook of the kernel for how its summation over several predecessors is still exercised).
 #pragma once
 
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -24,12 +28,17 @@ struct dim3 {
 };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct alignas(16) int4 { int32_t x, y, z, w; };
+static inline int4 make_int4(int32_t x, int32_t y, int32_t z, int32_t w) { return int4{x, y, z, w}; }
+struct alignas(8) uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
 #define __noinline__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(x) alignas(x)
@@ -219,6 +228,34 @@ inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned sh)
     sh = sh > 32u ? 32u : sh;
     return sh == 32u ? hi : __funnelshift_r(lo, hi, sh);
 }
+
+inline int __all_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) == 0xffffffffu; }
+inline int __any_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) != 0u; }
+inline void __syncwarp(unsigned = 0xffffffffu) { emul::wait(emul::my_warp().bar); }
+
+// one OS thread: a plain read-modify-write is atomic
+template <class T>
+inline T atomicAdd(T *p, T v)
+{
+    const T old = *p;
+    *p = old + v;
+    return old;
+}
+
+// the *_rn intrinsics: one IEEE operation each, round to nearest even (this TU is built with -ffp-contract=off, so
+// the compiler never fuses a * b + c on its own; fma / fmaf are the correctly rounded library functions)
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __double2float_rn(double a) { return (float)a; }
+inline int __double2hiint(double a) { return (int)(emul::to_bits(a) >> 32); }
+inline long long __double_as_longlong(double a) { return (long long)emul::to_bits(a); }
+inline int __float_as_int(float a) { return (int)(uint32_t)emul::to_bits(a); }
 
 // hook of chunk_codec.cuh: which tiles stay at their published aggregate (see the kernel)
 bool mbc_emul_keep_aggregate(uint32_t tile);

@@ -6,26 +6,16 @@ tiles, the aligned 16-byte word assembly and its ragged ends, the cut-off at n +
 has no GPU; `-m gpu` repeats the same shapes on the real device (tests/test_chunk_codec.py).  The emulator is
 test infrastructure, the product never builds it."""
 import ctypes as C
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-EMUL = os.path.join(HERE, "cuda_emul")
-CSRC = os.path.join(os.path.dirname(HERE), "distributedmandelbrot_b200", "csrc")
-SO = os.path.join(EMUL, "libcodec_emul.so")
+from test_escape_emulated import build_emulator
 
 
 @pytest.fixture(scope="module")
 def emul():
-    srcs = [os.path.join(EMUL, "codec_emul.cpp"), os.path.join(EMUL, "cuda_emul.h"), os.path.join(CSRC, "chunk_codec.cuh")]
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(s) for s in srcs):
-        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
-                               "-I", EMUL, "-I", CSRC, "-o", SO, srcs[0]], env=env)
-    lib = C.CDLL(SO)
+    lib = C.CDLL(build_emulator())           # one shared object for the serializer's and the escape kernels' emulation
     lib.emul_serialize_chunks.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                           C.c_int, C.c_uint]
     lib.emul_serialize_chunks.restype = C.c_int
