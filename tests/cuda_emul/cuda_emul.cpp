@@ -52,9 +52,20 @@ void switch_to(emul::Fiber *next)
 #endif
 }
 
+// Scheduling order.  0: round robin (deterministic).  Any other seed: every switch goes to a pseudo-randomly chosen
+// live fiber -- warps then overtake each other in ever different orders, so shared-memory traffic that lacks its
+// barrier shows up as a wrong result under some seed instead of passing by the luck of a fixed order.
+uint64_t g_sched_state = 0;
+
 emul::Fiber *next_live(emul::Fiber *from)
 {
-    const unsigned start = (unsigned)(from - g_fibers);
+    unsigned start = (unsigned)(from - g_fibers);
+    if (g_sched_state) {
+        g_sched_state ^= g_sched_state << 13;                // xorshift64
+        g_sched_state ^= g_sched_state >> 7;
+        g_sched_state ^= g_sched_state << 17;
+        start = (unsigned)(g_sched_state % g_nfibers);
+    }
     for (unsigned k = 1; k <= g_nfibers; ++k) {
         emul::Fiber *f = &g_fibers[(start + k) % g_nfibers];
         if (!f->done && f != from) return f;
@@ -84,6 +95,8 @@ extern "C" void emul_fiber_entry() { fiber_main(); }
 void fiber_entry_uc() { fiber_main(); }
 #endif
 }  // namespace
+
+extern "C" void emul_set_schedule(uint64_t seed) { g_sched_state = seed; }
 
 void emul::yield()
 {

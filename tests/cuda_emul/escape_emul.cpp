@@ -88,7 +88,61 @@ void run_points(const void *a)
     const auto *p = static_cast<const Points *>(a);
     mbk::escape_points_kernel<Real, kHead>(p->r, p->i, p->n, p->mrd, p->out);
 }
+struct U8Args {
+    const int32_t *counts;
+    uint8_t *out;
+    size_t n;
+    uint32_t mrd;
+};
+void run_counts_to_u8(const void *a)
+{
+    const auto *p = static_cast<const U8Args *>(a);
+    mbk::counts_to_u8_kernel(p->counts, p->out, p->n, p->mrd);
+}
+struct SumArgs {
+    const int32_t *counts;
+    size_t n;
+    uint32_t mrd;
+    unsigned long long *sum;
+};
+void run_useful(const void *a)
+{
+    const auto *p = static_cast<const SumArgs *>(a);
+    mbk::useful_iterations_kernel(p->counts, p->n, p->mrd, p->sum);
+}
+struct ClassArgs {
+    const uint8_t *p;
+    size_t n;
+    uint32_t *flags;
+};
+void run_classify(const void *a)
+{
+    const auto *p = static_cast<const ClassArgs *>(a);
+    mbk::classify_u8_kernel(p->p, p->n, p->flags);
+}
 }  // namespace
+
+// the small HBM-bound helpers (mb_counts_to_u8, mb_useful_iterations, mb_classify_u8), on a few CTAs
+extern "C" int emul_counts_to_u8(const int32_t *counts, uint8_t *out, size_t n, uint32_t mrd)
+{
+    U8Args a{counts, out, n, mrd};
+    emul::launch(dim3(3, 1, 1), 256, run_counts_to_u8, &a);
+    return 0;
+}
+extern "C" unsigned long long emul_useful_iterations(const int32_t *counts, size_t n, uint32_t mrd)
+{
+    unsigned long long sum = 0;
+    SumArgs a{counts, n, mrd, &sum};
+    emul::launch(dim3(3, 1, 1), 256, run_useful, &a);
+    return sum;
+}
+extern "C" int emul_classify_u8(const uint8_t *p, size_t n, uint32_t *flags)
+{
+    flags[0] = flags[1] = 1;                                  // DataChunk.cs:82,87: the kernel only clears
+    ClassArgs a{p, n, flags};
+    emul::launch(dim3(3, 1, 1), 256, run_classify, &a);
+    return 0;
+}
 
 extern "C" int emul_render_counts(const mb_tile *tiles, uint32_t n_tiles, int32_t *out, int dtype, unsigned long long *executed)
 {

@@ -211,3 +211,61 @@ def test_emulated_deep_zoom_rows_and_the_shortcut_s_accounting(emul, native, ora
             assert 0 < ex[0] < useful, (ex, useful)     # in-set pixels stop at their cycle, the others run as before
         u8 = _render(emul, native, [chunk.sub(0, y0, d, h, 0, d)], d * h, u8=True).reshape(h, d)
         assert np.array_equal(u8, oracle.counts_to_u8(want, mrd)), (sc, rf)
+
+
+def test_emulated_helper_kernels(emul, native, oracle, golden_meta, golden_arrays):
+    """counts_to_u8_kernel (.py:96-98 over a flat array, vector and scalar paths), useful_iterations_kernel,
+    classify_u8_kernel (DataChunk.IsNeverChunk / IsImmediateChunk)."""
+    emul.emul_counts_to_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32]
+    emul.emul_useful_iterations.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+    emul.emul_useful_iterations.restype = C.c_ulonglong
+    emul.emul_classify_u8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    for rec in golden_meta["u8"]:                                    # every count for 13 values of mrd, reference text
+        mrd = rec["mrd"]
+        counts = np.arange(mrd, dtype=np.int32)
+        out = np.empty(mrd, np.uint8)
+        emul.emul_counts_to_u8(counts.ctypes.data, out.ctypes.data, mrd, mrd)
+        assert np.array_equal(out, golden_arrays[rec["key"]]), mrd
+    counts = np.arange(1002, dtype=np.int32)[1:]                     # unaligned pointers take the scalar path
+    out = np.empty(1004, np.uint8)[3:]
+    emul.emul_counts_to_u8(counts.ctypes.data, out.ctypes.data, 1001, 1002)
+    assert np.array_equal(out, oracle.counts_to_u8(counts, 1002))
+    c = oracle.render_chunk_counts(10, 1024, 3, 5, 200).ravel()
+    assert emul.emul_useful_iterations(c.ctypes.data, c.size, 1024) == oracle.useful_iterations(c, 1024)
+    flags = np.zeros(2, np.uint32)
+    for payload, want in [(np.zeros(5000, np.uint8), [1, 0]), (np.ones(5000, np.uint8), [0, 1]),
+                          (np.r_[np.zeros(4999, np.uint8), np.uint8(1)], [0, 0]), (np.r_[np.uint8(0), np.ones(4999, np.uint8)], [0, 0])]:
+        emul.emul_classify_u8(payload.ctypes.data, payload.size, flags.ctypes.data)
+        assert flags.tolist() == want
+
+
+def test_emulated_kernels_under_random_warp_interleavings(emul, native, oracle, golden_meta, golden_arrays):
+    """The emulator's scheduler in random mode: at every barrier / warp collective the next fiber is drawn at random,
+    so the warps of a CTA overtake each other in a different order under every seed.  Results must not depend on it:
+    shared-memory traffic without its barrier (descriptor staging, the refill kernel's per-warp slots and patch
+    counter, the serializer's list / tile copy / look-back hand-over) would show up as a wrong result."""
+    import chunk_codec as codec
+    emul.emul_set_schedule.argtypes = [C.c_uint64]
+    emul.emul_serialize_chunks.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_uint]
+    rng = np.random.default_rng(21)
+    payload = np.ascontiguousarray(np.repeat(rng.integers(0, 4, 30_000).astype(np.uint8), rng.integers(1, 12, 30_000))[:70_001])
+    payload[20_000:40_000] = rng.integers(0, 256, 20_000)             # a tile denser than the list: two rounds
+    want_blob = codec.serialize(payload)
+    level, mrd, ir, ii, d = 10, 700, 3, 5, 96
+    want = oracle.render_chunk_counts(level, mrd, ir, ii, d)
+    try:
+        for seed in (0x9E3779B97F4A7C15, 12345, 777, 2**63 + 5, 31337):
+            emul.emul_set_schedule(seed)
+            for sc, rf in VARIANTS:
+                assert np.array_equal(_chunk(emul, native, level, mrd, ir, ii, d, shortcut=sc, refill=rf), want), (seed, sc, rf)
+            assert np.array_equal(_chunk(emul, native, level, mrd, ir, ii, d, u8=True, refill=True), oracle.counts_to_u8(want, mrd)), seed
+            n = payload.size
+            stride = (n + 1 + 255) // 256 * 256
+            out = np.full(stride, 0xEE, np.uint8)
+            info = np.zeros(32, np.uint8)
+            for spans in (1, 2):
+                assert emul.emul_serialize_chunks(payload.ctypes.data, n, 1, n, out.ctypes.data, stride, info.ctypes.data, 1, spans, 65535) == 0
+                assert out[:int(info[:8].view("<u8")[0])].tobytes() == want_blob, (seed, spans)
+    finally:
+        emul.emul_set_schedule(0)
