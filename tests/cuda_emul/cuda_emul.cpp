@@ -106,6 +106,7 @@ void emul::yield()
 
 void emul::launch(dim3 grid, unsigned threads, void (*fn)(const void *), const void *args)
 {
+    if (threads == 0 || threads > (unsigned)kMaxThreads || threads % 32u != 0) abort();   // whole warps only, as the kernels here launch
     g_block_dim = emul_uint3{threads, 1, 1};
     g_grid_dim = emul_uint3{grid.x, grid.y, grid.z};
     g_job = Job{grid, fn, args};
