@@ -210,3 +210,30 @@ def test_emulated_kernel_alignment_batches_and_threshold(emul, codec, oracle):
         want = codec.serialize(payload)
         assert blob == want, w
         assert int(info[4]) == codec.entry_type(payload)
+
+
+def test_emulated_kernel_random_run_structures(emul, codec):
+    """Property test (hypothesis): arbitrary mixtures of run lengths -- single bytes, short runs, runs of several
+    tiles -- at arbitrary sizes, input / output alignments, tile geometries and look-back modes serialise to exactly
+    the bytes of the restated reference serializer."""
+    from hypothesis import given, settings, strategies as st
+
+    run = st.one_of(st.integers(1, 3), st.integers(1, 3), st.integers(4, 40), st.integers(41, 3000), st.integers(8000, 40_000))
+    segment = st.tuples(st.lists(run, min_size=1, max_size=400), st.integers(0, 2**32 - 1))
+
+    @settings(max_examples=400, deadline=None, derandomize=True)
+    @given(st.lists(segment, min_size=1, max_size=6), st.integers(0, 15), st.integers(0, 15), st.sampled_from([1, 2]), st.sampled_from([0, 1, 2]),
+           st.integers(0, 70_000))
+    def check(segments, in_off, out_off, spans, keep, cut):
+        parts = []
+        for lens, seed in segments:
+            vals = np.random.default_rng(seed).integers(0, 256, len(lens)).astype(np.uint8)
+            parts.append(np.repeat(vals, lens))
+        p = np.concatenate(parts)
+        p = np.ascontiguousarray(p[:max(1, min(p.size, cut if cut else p.size, 120_000))])
+        (blob, info), = _serialize(emul, [p], keep=keep, in_off=in_off, out_off=out_off, spans=spans)
+        want = codec.serialize(p)
+        assert blob == want
+        assert int(info[2]) == 1 + int(np.count_nonzero(p[1:] != p[:-1]))
+
+    check()
