@@ -269,3 +269,17 @@ def test_emulated_kernels_under_random_warp_interleavings(emul, native, oracle, 
                 assert out[:int(info[:8].view("<u8")[0])].tobytes() == want_blob, (seed, spans)
     finally:
         emul.emul_set_schedule(0)
+
+
+def test_emulated_native_size_chunk_against_the_oracle_digest(emul, native, oracle, fullsize):
+    """A whole 4096 x 4096 DataChunk -- what process_workload renders -- of the BASELINE cfg4 frame (f64, mrd 10000) by
+    the CPU oracle's own digest (tests/golden/fullsize_cfg4.json): its cheapest chunk, 3.4e8 pixel-iterations over
+    131 072 CTAs.  (The boundary chunk (250, 420), 3.1e9 pixel-iterations, matches its digest too -- 31 s with the patch
+    kernel, 145 s with refill + shortcut -- and is left out for time.)"""
+    from distributedmandelbrot_b200.frame import CONFIGS
+    spec, doc, d = CONFIGS["cfg4"], fullsize("cfg4"), 4096
+    rec = {(r["ir"], r["ii"]): r for r in doc["chunks"].values()}[(246, 427)]
+    counts = _render(emul, native, [native.chunk_geometry(spec.level, 246, 427, d, spec.mrd)], d * d)
+    assert oracle.useful_iterations(counts, spec.mrd) == rec["useful"]
+    assert f"{oracle.fnv1a_words(counts):016x}" == rec["fnv"]
+    assert int(np.count_nonzero(counts == 0)) == rec["zeros"] and int(counts.max()) == rec["max"]
