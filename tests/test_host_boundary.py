@@ -109,6 +109,35 @@ def test_product_package_never_touches_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
 
 
+def test_product_build_never_uses_the_kernel_emulator(native):
+    """tests/cuda_emul runs the kernels' text on the CPU for the parity tests only: the product build never defines
+    MB_EMULATE, no product source outside the two guarded includes knows the emulator, and the shipped library
+    exports none of its entry points (there is no CPU execution path in the product)."""
+    import subprocess
+    from distributedmandelbrot_b200 import build
+    assert not any("MB_EMULATE" in flag for flag in build.NVCC_FLAGS)
+    pkg = os.path.join(ROOT, "distributedmandelbrot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "MB_EMULATE" not in txt and "cuda_emul" not in txt, f
+            elif f.endswith(".cuh"):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                # a kernel header may only name the emulator inside `#ifdef MB_EMULATE` ... `#else` / `#endif`
+                depth_emul = 0
+                for line in txt.splitlines():
+                    t = line.strip()
+                    if t.startswith("#ifdef MB_EMULATE"):
+                        depth_emul += 1
+                    elif depth_emul and (t.startswith("#else") or t.startswith("#endif")):
+                        depth_emul -= 1
+                    elif not t.startswith("//"):
+                        assert depth_emul or ("cuda_emul" not in t and "mbc_emul" not in t and "EMUL_" not in t), (f, line)
+    syms = subprocess.run(["nm", "-D", "--defined-only", build.SO], capture_output=True, text=True, check=True).stdout
+    assert "emul" not in syms
+
+
 def test_header_is_plain_c_and_links_from_c(native, tmp_path):
     """The boundary is a C ABI: include/mandelbrot_b200.h must compile as C99 and a C program must
     link against the library and call the host-only entry points (no GPU needed)."""
