@@ -144,6 +144,14 @@ extern "C" int emul_classify_u8(const uint8_t *p, size_t n, uint32_t *flags)
     return 0;
 }
 
+// the device's coordinate generator (in-kernel gen_arrays, .py:24-32) for every sample of one axis of a tile
+extern "C" void emul_tile_axis(const mb_tile *t, int axis, double *out)
+{
+    const uint32_t d1 = t->definition - 1u;
+    for (uint32_t k = 0; k < t->definition; ++k)
+        out[k] = axis == 0 ? mbk::linspace_at(k, d1, t->start_r, t->step_r, t->stop_r) : mbk::linspace_at(k, d1, t->start_i, t->step_i, t->stop_i);
+}
+
 extern "C" int emul_render_counts(const mb_tile *tiles, uint32_t n_tiles, int32_t *out, int dtype, unsigned long long *executed)
 {
     if (!tiles || !n_tiles || !out) return 1;

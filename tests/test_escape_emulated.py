@@ -24,14 +24,18 @@ VARIANTS = [(False, False), (True, False), (False, True), (True, True)]        #
 
 
 def build_emulator() -> str:
-    """g++ the kernels + the fiber runtime into one shared object (shared with tests/test_codec_emulated.py)."""
+    """g++ the kernels + the fiber runtime into one shared object (shared with tests/test_codec_emulated.py).
+    MB_EMUL_SO overrides it with a prebuilt one (scripts/mutation_check.py runs the suites against mutated kernels)."""
+    if os.environ.get("MB_EMUL_SO"):
+        return os.environ["MB_EMUL_SO"]
     deps = [os.path.join(EMUL, f) for f in SOURCES + ["cuda_emul.h"]] + \
            [os.path.join(CSRC, f) for f in ("chunk_codec.cuh", "escape_kernels.cuh", "escape_refill.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
-                               "-Wno-unused-but-set-variable", "-I", EMUL, "-I", CSRC, "-o", SO] + [os.path.join(EMUL, f) for f in SOURCES],
-                              env=env)
+        # -fsanitize=alignment: a misaligned 32- / 64- / 128-bit access is a fault on the device; x86 would let it pass
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fsanitize=alignment",
+                               "-fno-sanitize-recover=alignment", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-but-set-variable",
+                               "-I", EMUL, "-I", CSRC, "-o", SO] + [os.path.join(EMUL, f) for f in SOURCES], env=env)
     return SO
 
 
@@ -211,6 +215,67 @@ def test_emulated_deep_zoom_rows_and_the_shortcut_s_accounting(emul, native, ora
             assert 0 < ex[0] < useful, (ex, useful)     # in-set pixels stop at their cycle, the others run as before
         u8 = _render(emul, native, [chunk.sub(0, y0, d, h, 0, d)], d * h, u8=True).reshape(h, d)
         assert np.array_equal(u8, oracle.counts_to_u8(want, mrd)), (sc, rf)
+
+
+def test_emulated_escape_decided_by_the_last_unit_of_the_high_word(emul, native, oracle):
+    """tests/golden/threshold_points.json: the first escaping update is a block end (n = 8k) and |z|^2 there lies in
+    [4, 4 + 2^-18) -- `hi32(m) >= 0x40100000` holds with equality.  calc_mb_value (tested head of 32, then blocks) and
+    1 x 1 tiles through the patch and the refill kernels (blocks from the first update on), plain and with the shortcut."""
+    import json
+    pts = json.load(open(os.path.join(HERE, "golden", "threshold_points.json")))["points"]
+    r = np.array([float.fromhex(p["r"]) for p in pts])
+    i = np.array([float.fromhex(p["i"]) for p in pts])
+    n = np.array([p["n"] for p in pts], np.int32)
+    assert np.array_equal(_calc(emul, native, r, i, 301), n)
+    for mrd in (9, 25, 41, 49, 137):                                     # budgets that end right behind some of the escapes
+        assert np.array_equal(_calc(emul, native, r, i, mrd), np.where(n < mrd, n, 0)), mrd
+    for sc, rf in VARIANTS:
+        tiles = []
+        for k in range(len(pts)):
+            t = native.Tile()
+            t.start_r = t.stop_r = r[k]                                  # definition 1: numpy.linspace(start, stop, 1) = [start]
+            t.start_i = t.stop_i = i[k]
+            t.step_r = t.step_i = 0.0
+            t.definition, t.mrd, t.x0, t.y0, t.w, t.h = 1, 301, 0, 0, 1, 1
+            t.out_offset, t.out_pitch = k, 1
+            t.flags = (native.TILE_PERIOD_SHORTCUT if sc else 0) | (native.TILE_LANE_REFILL if rf else 0)
+            tiles.append(t)
+        assert np.array_equal(_render(emul, native, tiles, len(pts)), n), (sc, rf)
+
+
+def test_emulated_device_coordinates_equal_gen_arrays(emul, native, golden_meta, golden_arrays):
+    """linspace_at (the kernel's in-register replacement of gen_arrays, .py:19-37) for every sample of both axes:
+    the reference's own gen_arrays output (golden grids, incl. level 4 000 000) and numpy.linspace, with the forced
+    endpoint -- at shallow levels fl(fl((d-1) * step) + start) is often NOT `stop`."""
+    emul.emul_tile_axis.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    for rec in golden_meta["linspace"]:
+        t = native.chunk_geometry(rec["level"], rec["ir"], rec["ii"], rec["d"], 100)
+        for axis, key in ((0, "_r"), (1, "_i")):
+            out = np.empty(rec["d"], np.float64)
+            emul.emul_tile_axis(C.byref(t), axis, out.ctypes.data)
+            assert np.array_equal(out, golden_arrays[rec["key"] + key]), (rec, axis)
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        level = int(rng.integers(1, 5_000_000))
+        ir = int(rng.integers(0, level))
+        d = int(rng.choice([2, 3, 255, 256, 4096]))
+        t = native.chunk_geometry(level, ir, 0, d, 1)
+        out = np.empty(d, np.float64)
+        emul.emul_tile_axis(C.byref(t), 0, out.ctypes.data)
+        start = -2 + (4 / level) * ir
+        assert np.array_equal(out, np.linspace(start, start + 4 / level, d)), (level, ir, d)
+    # shallow levels, where the width of a chunk is comparable to its position: here the endpoint rule is visible
+    forced = 0
+    for level in range(1, 40):
+        for ir in range(level):
+            for d in (96, 160, 200, 257, 1000):
+                t = native.chunk_geometry(level, ir, 0, d, 1)
+                out = np.empty(d, np.float64)
+                emul.emul_tile_axis(C.byref(t), 0, out.ctypes.data)
+                start = -2 + (4 / level) * ir
+                assert np.array_equal(out, np.linspace(start, start + 4 / level, d)), (level, ir, d)
+                forced += int((d - 1) * t.step_r + t.start_r != t.stop_r)
+    assert forced > 50          # fl(fl((d-1) * step) + start) != stop in that many of these cases
 
 
 def test_emulated_helper_kernels(emul, native, oracle, golden_meta, golden_arrays):

@@ -181,6 +181,21 @@ def test_points_on_the_radius_2_circle(gpu, oracle):
         assert np.array_equal(got, oracle.render_chunk_counts(level, mrd, ir, ii, d)), (level, ir, ii)
 
 
+def test_escape_decided_by_the_last_unit_of_the_high_word(gpu, oracle):
+    """tests/golden/threshold_points.json (oracle/threshold_points.c): first escape at a block end with
+    4 <= |z|^2 < 4 + 2^-18, i.e. the kernel's integer compare `hi32(m) >= 0x40100000` holds with equality."""
+    import json
+    import os
+    from distributedmandelbrot_b200 import worker
+    pts = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "threshold_points.json")))["points"]
+    r = np.array([float.fromhex(p["r"]) for p in pts])
+    i = np.array([float.fromhex(p["i"]) for p in pts])
+    n = np.array([p["n"] for p in pts], np.int32)
+    assert np.array_equal(worker.calc_mb_value(r, i, 301), n)
+    for mrd in (9, 25, 41, 49, 137):
+        assert np.array_equal(worker.calc_mb_value(r, i, mrd), np.where(n < mrd, n, 0)), mrd
+
+
 def test_calc_mb_value_non_finite_and_huge_inputs(gpu, oracle):
     """The ufunc boundary accepts any float64: inf, NaN and coordinates far outside the plane must
     give what the literal loop gives (e.g. NaN >= 4 is False forever -> 0)."""

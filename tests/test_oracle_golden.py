@@ -233,3 +233,24 @@ def test_fullsize_fixture_matches_the_frame_table(oracle):
             assert int((got == 0).sum()) == rec["zeros"] and int(got.max()) == rec["max"]
             seen += 1
     assert seen > 0
+
+
+def test_threshold_points_fixture_is_what_the_oracle_says(oracle):
+    """tests/golden/threshold_points.json (oracle/threshold_points.c): coordinates whose first escaping update n is a
+    multiple of 8 with 4 <= |z|^2 < 4 + 2^-18 there -- the inputs on which the kernels' integer compare of the high
+    word is decided by its last unit, at a block end.  Scalar C oracle and the numpy restatement agree on every one."""
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "threshold_points.json")))
+    pts = doc["points"]
+    assert len(pts) >= 60 and sum(1 for p in pts if p["n"] >= 40) >= 15
+    r = np.array([float.fromhex(p["r"]) for p in pts])
+    i = np.array([float.fromhex(p["i"]) for p in pts])
+    n = np.array([p["n"] for p in pts], np.int32)
+    for k, p in enumerate(pts):
+        assert p["n"] % 8 == 0
+        assert oracle.escape_f64(r[k], i[k], 301) == p["n"]
+        assert oracle.escape_f64(r[k], i[k], p["n"]) == 0                 # one update short of it
+        m = float(p["m"])
+        assert 4.0 <= m < 4.0 + 2.0 ** -18
+    assert np.array_equal(oracle.np_counts(r, i, 301), n)
