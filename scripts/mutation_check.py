@@ -92,6 +92,25 @@ MUTANTS = [
      "if (save_point(n)) { sx = x; sy = y; }", "{ sx = x; sy = y; }", "equivalent"),
     ("escape: tiny-|c| inputs take the fused 2xy path", "escape_kernels.cuh",
      "return fabs(cr) <= 4.0 && fabs(ci) <= 4.0 && !tiny(cr) && !tiny(ci); }", "return fabs(cr) <= 4.0 && fabs(ci) <= 4.0; }", "escape"),
+    # ---- lane-refill kernel ----
+    ("refill: replay starts from the wrong block", "escape_refill.cuh",
+     "Real rx = tA ? sxx_ : mx_, ry = tA ? sy_ : my_;", "Real rx = tA ? mx_ : sxx_, ry = tA ? my_ : sy_;", "escape"),
+    ("refill: replayed escape index misses the first block's updates", "escape_refill.cuh",
+     "const int base = tA ? n : n + K;", "const int base = n;", "escape"),
+    ("refill: lanes near their update budget are not sent to the tested tail in time", "escape_refill.cuh",
+     "(lim - n < 4 * K));", "(lim - n < 2 * K));", "escape"),
+    ("refill: tested tail one update short", "escape_refill.cuh",
+     "                    for (int j = 1; j <= left; ++j) {", "                    for (int j = 1; j < left; ++j) {", "escape"),
+    ("refill: pixel handed to the wrong lane slot", "escape_refill.cuh", "const uint32_t q = pos + rank;", "const uint32_t q = pos + (rank ^ 1u);", "escape"),
+    ("refill: 128-bit row store repeats the third count", "escape_refill.cuh",
+     "*reinterpret_cast<int4 *>(dst) = make_int4(result, v1, v2, v3);", "*reinterpret_cast<int4 *>(dst) = make_int4(result, v1, v2, v2);", "escape"),
+    ("refill: descriptor slot read without the warp barriers around its refresh", "escape_refill.cuh",
+     "                __syncwarp();\n                if (lane < sizeof(mb_tile) / 8) {", "                if (lane < sizeof(mb_tile) / 8) {", "escape"),
+    ("refill: parked (periodic) lanes store a non-zero result", "escape_refill.cuh",
+     "        bool fin = pend;                                             // parked since an earlier trip: result 0\n        pend = false;\n        int result = 0;",
+     "        bool fin = pend;\n        int result = pend ? 1 : 0;\n        pend = false;", "escape"),
+    ("refill: short budgets (lim < 2K) enter deferred blocks", "escape_refill.cuh",
+     "if (lim < 2 * K || risky || !O::ordinary(cr, ci)) {", "if (risky || !O::ordinary(cr, ci)) {", "escape"),
     ("escape: fused uint8 row store drops the high half", "escape_kernels.cuh",
      "if ((lane & 7u) == 0) *reinterpret_cast<uint2 *>(gp) = make_uint2(v, hi);", "if ((lane & 7u) == 0) *reinterpret_cast<uint2 *>(gp) = make_uint2(v, v);", "escape"),
 ]
