@@ -92,6 +92,15 @@ MUTANTS = [
      "if (save_point(n)) { sx = x; sy = y; }", "{ sx = x; sy = y; }", "equivalent"),
     ("escape: tiny-|c| inputs take the fused 2xy path", "escape_kernels.cuh",
      "return fabs(cr) <= 4.0 && fabs(ci) <= 4.0 && !tiny(cr) && !tiny(ci); }", "return fabs(cr) <= 4.0 && fabs(ci) <= 4.0; }", "escape"),
+    ("escape f32: per-update test misses m == 4.0f exactly", "escape_kernels.cuh",
+     "static __device__ __forceinline__ bool escaped(float m) { return __float_as_int(m) >= 0x40800000; }",
+     "static __device__ __forceinline__ bool escaped(float m) { return __float_as_int(m) > 0x40800000; }", "escape"),
+    ("escape f32: block-end test misses m == 4.0f exactly", "escape_kernels.cuh",
+     "static __device__ __forceinline__ bool tripped(float m) { return !(m < 4.0f); }",
+     "static __device__ __forceinline__ bool tripped(float m) { return !(m <= 4.0f); }", "escape"),
+    ("escape f32: block-end test written as m >= 4 (an overflow to NaN would read as not escaped)", "escape_kernels.cuh",
+     "static __device__ __forceinline__ bool tripped(float m) { return !(m < 4.0f); }",
+     "static __device__ __forceinline__ bool tripped(float m) { return m >= 4.0f; }", "escape"),
     # ---- lane-refill kernel ----
     ("refill: replay starts from the wrong block", "escape_refill.cuh",
      "Real rx = tA ? sxx_ : mx_, ry = tA ? sy_ : my_;", "Real rx = tA ? mx_ : sxx_, ry = tA ? my_ : sy_;", "escape"),

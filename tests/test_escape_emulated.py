@@ -241,6 +241,24 @@ def test_emulated_escape_decided_by_the_last_unit_of_the_high_word(emul, native,
             t.flags = (native.TILE_PERIOD_SHORTCUT if sc else 0) | (native.TILE_LANE_REFILL if rf else 0)
             tiles.append(t)
         assert np.array_equal(_render(emul, native, tiles, len(pts)), n), (sc, rf)
+    # binary32: |z|^2 == 4.0f exactly at a multiple of 16 (blocks of 16, block-end test `!(m < 4)`)
+    p32 = json.load(open(os.path.join(HERE, "golden", "threshold_points.json")))["points_f32"]
+    r32 = np.array([float.fromhex(p["r"]) for p in p32])
+    i32 = np.array([float.fromhex(p["i"]) for p in p32])
+    n32 = np.array([p["n"] for p in p32], np.int32)
+    assert np.array_equal(_calc(emul, native, r32, i32, 301, dtype="f32"), n32)
+    for sc, rf in VARIANTS:
+        tiles = []
+        for k in range(len(p32)):
+            t = native.Tile()
+            t.start_r = t.stop_r = r32[k]
+            t.start_i = t.stop_i = i32[k]
+            t.step_r = t.step_i = 0.0
+            t.definition, t.mrd, t.x0, t.y0, t.w, t.h = 1, 301, 0, 0, 1, 1
+            t.out_offset, t.out_pitch = k, 1
+            t.flags = (native.TILE_PERIOD_SHORTCUT if sc else 0) | (native.TILE_LANE_REFILL if rf else 0)
+            tiles.append(t)
+        assert np.array_equal(_render(emul, native, tiles, len(p32), dtype="f32"), n32), (sc, rf)
 
 
 def test_emulated_device_coordinates_equal_gen_arrays(emul, native, golden_meta, golden_arrays):

@@ -254,3 +254,13 @@ def test_threshold_points_fixture_is_what_the_oracle_says(oracle):
         m = float(p["m"])
         assert 4.0 <= m < 4.0 + 2.0 ** -18
     assert np.array_equal(oracle.np_counts(r, i, 301), n)
+    # binary32: first escape at a multiple of 16 with |z|^2 == 4.0f exactly (the block-end test there is `!(m < 4)`)
+    p32 = doc["points_f32"]
+    assert len(p32) >= 8
+    for p in p32:
+        cr, ci = float.fromhex(p["r"]), float.fromhex(p["i"])
+        assert np.float32(cr) == cr and np.float32(ci) == ci and p["n"] % 16 == 0
+        assert oracle.lib().mbo_escape_f32(cr, ci, 301) == p["n"] and oracle.lib().mbo_escape_f32(cr, ci, p["n"]) == 0
+    r32 = np.array([float.fromhex(p["r"]) for p in p32])
+    i32 = np.array([float.fromhex(p["i"]) for p in p32])
+    assert np.array_equal(oracle.np_counts(r32, i32, 301, dtype=np.float32), np.array([p["n"] for p in p32], np.int32))
