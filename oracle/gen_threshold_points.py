@@ -23,12 +23,18 @@ SEARCHES = [  # r0 r1 i0 i1 points-per-thread mrd type
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden", "threshold_points.json"))
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the points per thread (a quick try: 0.05)")
+    opts = ap.parse_args()
     exe = os.path.join(tempfile.mkdtemp(prefix="thr_"), "threshold_points")
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", exe, os.path.join(HERE, "threshold_points.c")], env=env)
     env.setdefault("OMP_NUM_THREADS", "8")
     p64, p32, seen = [], [], set()
     for args in SEARCHES:
+        args = (*args[:4], str(max(1, int(int(args[4]) * opts.scale))), *args[5:])
         out = subprocess.run([exe, *args], env=env, capture_output=True, text=True, check=True).stdout
         for line in out.splitlines():
             f = line.split()
@@ -47,7 +53,7 @@ def main():
     doc = {"generator": "oracle/threshold_points.c: strict arithmetic of .py:44-68; binary64 points: first escaping update n = 8k with "
                         "hi32(|z|^2) == 0x40100000; binary32 points (coordinates are binary32 values): n = 16k with |z|^2 == 4.0f exactly",
            "points": p64, "points_f32": p32}
-    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "threshold_points.json")
+    path = opts.out
     json.dump(doc, open(path, "w"), indent=0)
     print(f"{len(p64)} binary64 and {len(p32)} binary32 points -> {path}")
 
